@@ -1,0 +1,166 @@
+/*
+ * arx.h -- C ABI of the B200-native ISBFSAR action-recognition scoring path.
+ *
+ * The reference (steb6/ISBFSAR) has no native/FFI boundary: the path sits behind
+ * its Python API (modules/ar/utils/model.py, modules/ar/ar.py).  This header is
+ * the boundary a binding would use; isbfsar_b200/_lib.py binds it with ctypes
+ * and isbfsar_b200/{model,ar}.py mirror the reference classes on top of it.
+ * Each entry point cites the reference code it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative arx_status; nothing
+ *     throws across the boundary; arx_last_error() gives the message.
+ *   - all pointers named *_dev are CUDA device pointers on the handle's device,
+ *     fp32 unless stated, C-contiguous in the reference's own layouts.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as
+ *     void*); no hidden synchronisation except in the *_host entry points.
+ *   - the caller owns every I/O buffer; the handle owns weight copies, the
+ *     support-set operands and the scratch workspace.  One handle per device,
+ *     not thread-safe (the reference is single-threaded, main.py:111).
+ *   - inference only (the reference calls it under torch.no_grad(), ar.py:68).
+ */
+#ifndef ARX_H
+#define ARX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARX_ABI_VERSION 1
+#if defined(__GNUC__)
+#define ARX_API __attribute__((visibility("default")))
+#else
+#define ARX_API
+#endif
+#define ARX_MAX_TRANSFORMERS 4
+
+typedef enum arx_status {
+  ARX_OK = 0,
+  ARX_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  ARX_ERR_CUDA = -2,      /* a CUDA runtime call failed               */
+  ARX_ERR_STATE = -3,     /* call order (weights/support not set)     */
+  ARX_ERR_NOMEM = -4
+} arx_status;
+
+/* Mirror of the TRXConfig fields the path reads (utils/params.py:50-95). */
+typedef struct arx_config {
+  int32_t seq_len;        /* T; 16 (utils/params.py:8)                                   */
+  int32_t n_joints;       /* J; MLP input = 3*J, hidden = 6*J (model.py:269)             */
+  int32_t feat_dim;       /* F = trans_linear_in_dim = MLP output = 256                  */
+  int32_t out_dim;        /* D = trans_linear_out_dim = 128                              */
+  int32_t n_transformers; /* len(temp_set) (model.py:279)                                */
+  int32_t cardinality[ARX_MAX_TRANSFORMERS]; /* temp_set entries, 2 or 3                 */
+  int32_t has_discriminator; /* 1 for model="DISC" (model.py:282-285)                    */
+  int32_t max_chunk;      /* windows processed per internal pass (0 = default)           */
+  int32_t force_path;     /* 0 = auto, 1 = fp32 CUDA-core kernels, 2 = tcgen05 kernels   */
+} arx_config;
+
+/* Weights in the reference state_dict layouts; host or device fp32. */
+typedef struct arx_weights {
+  int32_t on_device;                     /* 1: pointers are device pointers             */
+  const float *fc1_w, *fc1_b;            /* features_extractor.sk.fc1 (6J,3J),(6J)      */
+  const float *fc2_w, *fc2_b;            /* features_extractor.sk.fc2 (F,6J),(F)        */
+  const float *pe[ARX_MAX_TRANSFORMERS];     /* transformers.i.pe.pe (1,int(1.5T),F)    */
+  const float *k_w[ARX_MAX_TRANSFORMERS];    /* transformers.i.k_linear.weight (D,c*F)  */
+  const float *k_b[ARX_MAX_TRANSFORMERS];
+  const float *v_w[ARX_MAX_TRANSFORMERS];    /* transformers.i.v_linear.weight (D,c*F)  */
+  const float *v_b[ARX_MAX_TRANSFORMERS];
+  const float *ln_g[ARX_MAX_TRANSFORMERS];   /* transformers.i.norm_k.weight (D)        */
+  const float *ln_b[ARX_MAX_TRANSFORMERS];
+  const float *dr_w, *dr_b;              /* discriminator.dimensionality_reduction (T,D)*/
+  const float *d1_w, *d1_b;              /* discriminator.fc1 (256, C(T,2)*T)           */
+  const float *d2_w, *d2_b;              /* discriminator.fc2 (64,256)                  */
+  const float *d3_w, *d3_b;              /* discriminator.fc3 (1,64)                    */
+} arx_weights;
+
+typedef struct arx_handle arx_handle;
+
+/* TRXOS.__init__ (model.py:261-289): allocate a scorer on the current CUDA device. */
+ARX_API int arx_create(const arx_config *cfg, arx_handle **out);
+ARX_API void arx_destroy(arx_handle *h);
+ARX_API const char *arx_last_error(const arx_handle *h);   /* h may be NULL: last create error */
+ARX_API int arx_abi_version(void);
+
+/* nn.Module.load_state_dict for the skeleton path (ar.py:17-19). */
+ARX_API int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream);
+
+/* TemporalCrossTransformer.__init__ tuple table (model.py:51-55): writes the
+ * C(T,c) x c lexicographic combinations as int32, built on device. */
+ARX_API int arx_tuple_count(const arx_handle *h, int32_t ti);
+ARX_API int arx_tuple_table(arx_handle *h, int32_t ti, int32_t *out_dev, void *stream);
+
+/* MLP.forward (model.py:164-180) over n_frames rows of 3J -> F. */
+ARX_API int arx_embed(arx_handle *h, const float *frames_dev, int64_t n_frames, float *feats_dev, void *stream);
+
+/* Support side of TemporalCrossTransformer.forward (model.py:65,69,71,75,77,81)
+ * done ONCE per support-set change instead of per call (ar.py:56-67).
+ *   poses_dev (W,T,3J) -> MLP -> features; or feats_dev (W,T,F) given directly
+ *   (the ss_features argument of TRXOS.forward, model.py:291,307).
+ * Class order is the caller's (ss_labels[0] already applied). */
+ARX_API int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, void *stream);
+ARX_API int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way, void *stream);
+/* out (W,T,F): the 'support_features' entry of the return dict (model.py:327-328). */
+ARX_API int arx_get_support_features(arx_handle *h, float *feats_dev, void *stream);
+ARX_API int arx_support_way(const arx_handle *h);
+
+/* Support operands as one flat device blob, for NCCL broadcast across ranks
+ * (SURVEY.md 8e).  export/import must use handles with identical config+weights. */
+ARX_API int64_t arx_support_blob_bytes(const arx_handle *h, int32_t way);
+ARX_API int arx_export_support(arx_handle *h, void *blob_dev, void *stream);
+ARX_API int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *stream);
+
+/* TRXOS.forward (model.py:291-328) for B query windows against the current
+ * support set, transformers[0] + discriminator:
+ *   query_dev (B,T,3J) -> logits_dev (B,W) [= -distance], is_true_dev (B) in (0,1)
+ *   [may be NULL / ignored without discriminator], chosen_dev (B) int32 argmax
+ *   (first maximum on ties, model.py:323) [may be NULL]. */
+ARX_API int arx_score(arx_handle *h, const float *query_dev, int64_t n_windows,
+              float *logits_dev, float *is_true_dev, int32_t *chosen_dev, void *stream);
+
+/* TemporalCrossTransformer(args, temp_set[ti]).forward(...)['logits'] (model.py:59-148)
+ * from precomputed frame features qfeats_dev (B,T,F); used for the cardinality-3
+ * transformer that TRXOS.forward never calls (model.py:320). */
+ARX_API int arx_score_features(arx_handle *h, int32_t ti, const float *qfeats_dev, int64_t n_windows,
+                       float *logits_dev, void *stream);
+
+/* Debug outputs (model.py:110-111,126,146): softmax scores P (B,W,N,N) and
+ * prototypes (B,W,N,D) of transformers[0] for a SMALL batch; either may be NULL. */
+ARX_API int arx_debug_attention(arx_handle *h, const float *query_dev, int64_t n_windows,
+                        float *probs_dev, float *prototypes_dev, void *stream);
+
+/* End-to-end convenience: HOST buffers in, HOST buffers out; chunks are staged
+ * through pinned memory with copies overlapped with compute.  Synchronises. */
+ARX_API int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows,
+                   float *logits_host, float *is_true_host, int32_t *chosen_host);
+
+/* MetrABS-style heatmap decode (modules/hpe/hpe.py:108-169 + main.py:103-105):
+ *   logits_dev (B,8,8,32+8*32) fp32 -> poses_dev (B,3*n_out) fp32 root-centred,
+ *   valid_dev (B) uint8 (0 where the reference returns None, hpe.py:152-153).
+ *   expand_dev (32,n_out) fp32 = column-selected assets/32_to_122.npy,
+ *   new_K (3x3 row-major) and homo_inv (3x3) as produced by misc.py:homography. */
+ARX_API int arx_decode_heatmaps(arx_handle *h, const float *logits_dev, int64_t n_frames,
+                        const float *expand_dev, int32_t n_out,
+                        const float *new_K_host9, const float *homo_inv_host9,
+                        float *poses_dev, uint8_t *valid_dev, void *stream);
+
+/* Stage timers for roofline reporting: CUDA events recorded on the caller's stream around the
+ * stages of arx_score (0 frame embedding MLP, 1 per-frame K/V projection, 2 tuple build + LayerNorm,
+ * 3 cross-attention + distances, 4 open-set head).  arx_profile_read synchronises the events,
+ * adds the elapsed milliseconds per stage into ms[ARX_N_STAGES] and returns the number of
+ * arx_score chunks covered in *chunks; reset != 0 clears the accumulators. */
+#define ARX_N_STAGES 5
+ARX_API int arx_profile_enable(arx_handle *h, int32_t on);
+ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset);
+
+/* Introspection for tests/bench: kernel launches issued by this handle so far,
+ * and which attention path the last arx_score used (1 = fp32, 2 = tcgen05). */
+ARX_API int64_t arx_launch_count(const arx_handle *h);
+ARX_API int arx_last_path(const arx_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARX_H */

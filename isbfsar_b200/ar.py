@@ -1,0 +1,105 @@
+"""Drop-in for the reference's `modules/ar/ar.py` (ActionRecognizer, ar.py:10-96).
+
+Same constructor, attribute surface (`support_set`, `requires_focus`, `previous_frames`, `seq_len`,
+`way`, `n_joints`, `input_type`, `device`) and `inference` / `train` / `remove` behaviour, including the
+sentinel returns and the per-class `"features"` cache that `main.py:321-333` pickles.  The support-side
+tuple operands are precomputed on the device once per support-set change instead of on every frame.
+"""
+from __future__ import annotations
+
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .model import TRXOS
+from .params import TRXConfig
+
+
+class ActionRecognizer:
+    def __init__(self, args, add_hook=False, state_dict=None):
+        """`args` as in the reference (a TRXConfig-like object).  The checkpoint at `args.final_ckpt_path`
+        is loaded like ar.py:17-19 (`'model_state_dict'`, `.module` infixes stripped); `state_dict` may be
+        passed directly instead (extension used by tests, no file needed)."""
+        self.input_type = args.input_type
+        self.device = args.device
+        cfg = args if hasattr(args, "temp_set") else TRXConfig()
+        self.ar = TRXOS(cfg, add_hook=add_hook)
+        if state_dict is None:
+            state_dict = torch.load(args.final_ckpt_path, map_location="cpu")["model_state_dict"]
+        state_dict = OrderedDict({k.replace(".module", ""): v for k, v in state_dict.items()})
+        own = self.ar.state_dict()
+        # post_resnet (rgb-only) may be absent from skeleton-only checkpoints; everything else is required
+        missing = [k for k in own if k not in state_dict and not k.startswith("post_resnet.")]
+        if missing:
+            raise KeyError(f"checkpoint is missing {missing}")
+        self.ar.load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=False)
+        self.ar.cuda()
+        self.ar.eval()
+
+        self.support_set = OrderedDict()
+        self.requires_focus = {}
+        self.previous_frames = []
+        self.seq_len = args.seq_len
+        self.way = args.way
+        self.n_joints = args.n_joints if args.input_type == "skeleton" else 0
+        self._support_key = None
+
+    # the support operands on the device are valid for exactly this identity of the support set
+    def _current_key(self):
+        return tuple((k, id(v.get("poses")), id(v.get("features"))) for k, v in self.support_set.items())
+
+    def inference(self, data):
+        """ar.py:30-84.  data = {"sk": ndarray (3J,)}.  Returns (results, open_set_result, requires_focus)."""
+        if data is None or len(data) == 0:
+            return {}, 0, {}
+        if len(self.support_set) == 0:
+            return {}, 0, {}
+        data = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32).cuda() for k, v in data.items()}
+        self.previous_frames.append(copy.copy(data))
+        if len(self.previous_frames) < self.seq_len:
+            return {}, 0, {}
+        elif len(self.previous_frames) == self.seq_len + 1:
+            self.previous_frames = self.previous_frames[1:]
+        query = torch.stack([f["sk"] for f in self.previous_frames]).unsqueeze(0)     # (1,T,3J)
+
+        key = self._current_key()
+        if key != self._support_key:
+            names = list(self.support_set.keys())
+            if all("features" in self.support_set[c] for c in names):
+                # ar.py:56-61 -- cached features (zero padding up to `way` never reaches the scorer: only
+                # the real classes are labelled, ar.py:51)
+                feats = torch.stack([self.support_set[c]["features"] for c in names])
+                self.ar.set_support(features=feats)
+            else:
+                poses = torch.stack([self.support_set[c]["poses"] for c in names])
+                self.ar.set_support(poses=poses)
+                feats = self.ar.support_features()
+                for i, c in enumerate(names):                                           # ar.py:72-74
+                    self.support_set[c]["features"] = feats[i]
+            self._support_key = self._current_key()
+
+        logits, is_true = self.ar.score(query)
+        few_shot_result = torch.softmax(logits.squeeze(0), dim=0).cpu().numpy()        # ar.py:77
+        open_set_result = is_true.squeeze(0).cpu().numpy()                             # ar.py:78
+        results = {}
+        for k, name in enumerate(self.support_set.keys()):
+            results[name] = few_shot_result[k]
+        return results, open_set_result, self.requires_focus
+
+    def remove(self, flag):
+        """ar.py:86-92"""
+        if flag in self.support_set.keys():
+            self.support_set.pop(flag)
+            self.requires_focus.pop(flag)
+            self._support_key = None
+            return True
+        return False
+
+    def train(self, inp):
+        """ar.py:94-96.  inp = {"flag": str, "data": {"poses": (T,3J)}, "requires_focus": bool}"""
+        self.support_set[inp["flag"]] = {c: torch.as_tensor(np.asarray(inp["data"][c]), dtype=torch.float32).cuda()
+                                         for c in inp["data"].keys()}
+        self.requires_focus[inp["flag"]] = inp["requires_focus"]
+        self._support_key = None

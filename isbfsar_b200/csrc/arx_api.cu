@@ -1,0 +1,597 @@
+// C ABI (include/arx.h): handle management, weight staging, support-set precompute and the
+// scoring orchestration.  Host-side only; every kernel lives in the other translation units.
+#include "arx_internal.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+
+static std::string g_create_err;
+
+int arx_fail(arx_handle *h, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_err = buf;
+  return code;
+}
+
+int arx_ws_reserve(arx_handle *h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return ARX_OK;
+  if (h->ws) {
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    ARX_CUDA(h, cudaFree(h->ws));
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+  }
+  size_t want = bytes + (bytes >> 3);
+  cudaError_t e = cudaMalloc(&h->ws, want);
+  if (e != cudaSuccess) {
+    want = bytes;
+    e = cudaMalloc(&h->ws, want);
+  }
+  if (e != cudaSuccess) return arx_fail(h, ARX_ERR_NOMEM, "workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  h->ws_bytes = want;
+  return ARX_OK;
+}
+
+namespace {
+
+struct Carver {
+  char *base;
+  size_t off = 0;
+  explicit Carver(void *p) : base(static_cast<char *>(p)) {}
+  template <class Tp> Tp *take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    Tp *p = base ? reinterpret_cast<Tp *>(base + off) : nullptr;
+    off += n * sizeof(Tp);
+    return p;
+  }
+};
+
+long long comb(int n, int k) {
+  if (k < 0 || k > n) return 0;
+  long long r = 1;
+  for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+  return r;
+}
+
+template <class Tp> int dev_alloc(arx_handle *h, Tp **p, size_t n) {
+  ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(Tp)));
+  return ARX_OK;
+}
+
+int upload(arx_handle *h, float *dst, const float *src, size_t n, bool on_device, cudaStream_t st) {
+  if (!src) return arx_fail(h, ARX_ERR_INVALID, "load_weights: missing tensor");
+  ARX_CUDA(h, cudaMemcpyAsync(dst, src, n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  return ARX_OK;
+}
+
+void free_support(arx_handle *h) {
+  for (int i = 0; i < h->cfg.n_transformers; ++i) {
+    cudaFree(h->tr[i].ks); cudaFree(h->tr[i].vs);
+    cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img);
+    h->tr[i].ks = h->tr[i].vs = nullptr;
+    h->tr[i].ks_img = h->tr[i].vs_img = nullptr;
+  }
+  cudaFree(h->ss_feat);
+  h->ss_feat = nullptr;
+  h->way = h->way_cap = 0;
+}
+
+// per-window workspace of the fp32 path
+struct Fp32Ws {
+  float *H1, *FE, *G, *Kq, *Vq, *Z, *partial, *y, *h1, *h2;
+  size_t bytes;
+};
+Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, void *base) {
+  Carver c(base);
+  Fp32Ws w{};
+  const int nb = (tr.N + 63) / 64;
+  w.H1 = from_frames ? c.take<float>(n * h->T * h->H) : nullptr;
+  w.FE = from_frames ? c.take<float>(n * h->T * h->F) : nullptr;
+  w.G = c.take<float>(n * h->T * 2 * tr.c * h->D);
+  w.Kq = c.take<float>(n * tr.N * h->D);
+  w.Vq = c.take<float>(n * tr.N * h->D);
+  w.Z = c.take<float>(n * way * tr.N * 2);
+  w.partial = c.take<float>(n * way * nb);
+  w.y = disc ? c.take<float>(n * tr.N * h->T) : nullptr;
+  w.h1 = disc ? c.take<float>(n * 256) : nullptr;
+  w.h2 = disc ? c.take<float>(n * 64) : nullptr;
+  w.bytes = c.off + 256;
+  return w;
+}
+
+int64_t pick_chunk(arx_handle *h, const ArxTransformer &tr, int way, bool from_frames, bool disc, int64_t n_total) {
+  Fp32Ws one = carve_fp32(h, tr, 1, way, from_frames, disc, nullptr);
+  int64_t cap = h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096;
+  const size_t budget = (size_t)3 << 30;
+  int64_t fit = (int64_t)(budget / one.bytes);
+  if (fit < 1) fit = 1;
+  return std::max<int64_t>(1, std::min<int64_t>(std::min(cap, fit), n_total));
+}
+
+// frames (n_seq*T, 3J) -> features (n_seq*T, F)             (model.py:164-180)
+int embed_frames(arx_handle *h, const float *X, int64_t rows, float *H1, float *FE, cudaStream_t st) {
+  int rc = arx_fp32_linear(h, X, h->J3, h->fc1_w, h->J3, h->fc1_b, H1, h->H, rows, h->H, h->J3, ARX_ACT_RELU, nullptr, 1, st);
+  if (rc) return rc;
+  return arx_fp32_linear(h, H1, h->H, h->fc2_w, h->H, h->fc2_b, FE, h->F, rows, h->F, h->H, ARX_ACT_RELU, nullptr, 1, st);
+}
+
+// features -> per-frame projections with the positional encoding folded into a per-position bias
+// table: (f + pe[t]).Wp^T + bp = f.Wp^T + (pe[t].Wp^T + bp)   (model.py:65-66,75-78)
+int project_frames(arx_handle *h, const ArxTransformer &tr, const float *FE, int64_t rows, float *G, cudaStream_t st) {
+  return arx_fp32_linear(h, FE, h->F, tr.wp, h->F, nullptr, G, 2 * tr.c * h->D, rows, 2 * tr.c * h->D, h->F, ARX_ACT_NONE,
+                         tr.bp /* (T, 2cD) table */, h->T, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int arx_abi_version(void) { return ARX_ABI_VERSION; }
+
+const char *arx_last_error(const arx_handle *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int arx_create(const arx_config *cfg, arx_handle **out) {
+  if (!cfg || !out) return arx_fail(nullptr, ARX_ERR_INVALID, "arx_create: null argument");
+  *out = nullptr;
+  if (cfg->seq_len < 2 || cfg->seq_len > 64) return arx_fail(nullptr, ARX_ERR_INVALID, "seq_len %d out of range [2,64]", cfg->seq_len);
+  if (cfg->out_dim != 128) return arx_fail(nullptr, ARX_ERR_INVALID, "trans_linear_out_dim must be 128 (got %d)", cfg->out_dim);
+  if (cfg->feat_dim <= 0 || cfg->feat_dim % 4) return arx_fail(nullptr, ARX_ERR_INVALID, "feat_dim must be a positive multiple of 4");
+  if (cfg->n_joints <= 0) return arx_fail(nullptr, ARX_ERR_INVALID, "n_joints must be positive");
+  if (cfg->n_transformers < 1 || cfg->n_transformers > ARX_MAX_TRANSFORMERS)
+    return arx_fail(nullptr, ARX_ERR_INVALID, "n_transformers out of range");
+  for (int i = 0; i < cfg->n_transformers; ++i)
+    if (cfg->cardinality[i] < 1 || cfg->cardinality[i] > 4 || cfg->cardinality[i] > cfg->seq_len)
+      return arx_fail(nullptr, ARX_ERR_INVALID, "temp_set[%d]=%d unsupported", i, cfg->cardinality[i]);
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return arx_fail(nullptr, ARX_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return arx_fail(nullptr, ARX_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return arx_fail(nullptr, ARX_ERR_INVALID, "libarx is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+  arx_handle *h = new arx_handle();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  h->T = cfg->seq_len;
+  h->J3 = cfg->n_joints * 3;
+  h->H = cfg->n_joints * 6;
+  h->F = cfg->feat_dim;
+  h->D = cfg->out_dim;
+  int rc = ARX_OK;
+  auto A = [&](float **p, size_t n) { if (rc == ARX_OK) rc = dev_alloc(h, p, n); };
+  A(&h->fc1_w, (size_t)h->H * h->J3); A(&h->fc1_b, h->H);
+  A(&h->fc2_w, (size_t)h->F * h->H); A(&h->fc2_b, h->F);
+  for (int i = 0; i < cfg->n_transformers && rc == ARX_OK; ++i) {
+    ArxTransformer &tr = h->tr[i];
+    tr.c = cfg->cardinality[i];
+    tr.N = (int)comb(h->T, tr.c);
+    tr.Npad = (tr.N + 127) / 128 * 128;
+    A(&tr.pe, (size_t)h->T * h->F);
+    A(&tr.wp, (size_t)2 * tr.c * h->D * h->F);
+    A(&tr.bp, (size_t)h->T * 2 * tr.c * h->D);
+    A(&tr.ln_g, h->D); A(&tr.ln_b, h->D);
+    if (rc == ARX_OK) rc = dev_alloc(h, &tr.tuples, (size_t)tr.N * tr.c);
+    if (rc == ARX_OK) rc = arx_build_tuple_table(h, h->T, tr.c, tr.N, tr.tuples, 0);
+  }
+  if (cfg->has_discriminator) {
+    const int n2 = h->T * (h->T - 1) / 2;
+    A(&h->dr_w, (size_t)h->T * h->D); A(&h->dr_b, h->T);
+    A(&h->d1_w, (size_t)256 * n2 * h->T); A(&h->d1_b, 256);
+    A(&h->d2_w, 64 * 256); A(&h->d2_b, 64);
+    A(&h->d3_w, 64); A(&h->d3_b, 1);
+  }
+  if (rc == ARX_OK && cudaDeviceSynchronize() != cudaSuccess) rc = arx_fail(h, ARX_ERR_CUDA, "create: sync failed");
+  if (rc != ARX_OK) {
+    g_create_err = h->err;
+    arx_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return ARX_OK;
+}
+
+void arx_destroy(arx_handle *h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  free_support(h);
+  cudaFree(h->fc1_w); cudaFree(h->fc1_b); cudaFree(h->fc2_w); cudaFree(h->fc2_b);
+  for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
+    ArxTransformer &tr = h->tr[i];
+    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples);
+  }
+  cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
+  cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
+  cudaFree(h->ws);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]);
+    if (h->own_stream[i]) cudaStreamDestroy(h->own_stream[i]);
+    if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+  }
+  delete h;
+}
+
+int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
+  if (!h || !w) return arx_fail(h, ARX_ERR_INVALID, "load_weights: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool od = w->on_device != 0;
+  int rc;
+#define UP(dst, src, n) if ((rc = upload(h, dst, src, (n), od, st)) != ARX_OK) return rc
+  UP(h->fc1_w, w->fc1_w, (size_t)h->H * h->J3); UP(h->fc1_b, w->fc1_b, h->H);
+  UP(h->fc2_w, w->fc2_w, (size_t)h->F * h->H); UP(h->fc2_b, w->fc2_b, h->F);
+  const int maxlen = (int)(h->T * 1.5);
+  (void)maxlen;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) {
+    ArxTransformer &tr = h->tr[i];
+    const int D = h->D, F = h->F, c = tr.c;
+    UP(tr.pe, w->pe[i], (size_t)h->T * F);                 // first T rows of (1, int(1.5T), F) (model.py:27)
+    UP(tr.ln_g, w->ln_g[i], D); UP(tr.ln_b, w->ln_b[i], D);
+    if (!w->k_w[i] || !w->v_w[i] || !w->k_b[i] || !w->v_b[i]) return arx_fail(h, ARX_ERR_INVALID, "load_weights: transformer %d tensors missing", i);
+    // wp rows [p*D,(p+1)*D) = k_linear.weight[:, p*F:(p+1)*F]; rows [(c+p)*D, ...) = v_linear.weight[:, p*F:(p+1)*F]
+    const cudaMemcpyKind kind = od ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int p = 0; p < c; ++p) {
+      ARX_CUDA(h, cudaMemcpy2DAsync(tr.wp + (size_t)p * D * F, F * sizeof(float), w->k_w[i] + (size_t)p * F, (size_t)c * F * sizeof(float),
+                                    F * sizeof(float), D, kind, st));
+      ARX_CUDA(h, cudaMemcpy2DAsync(tr.wp + (size_t)(c + p) * D * F, F * sizeof(float), w->v_w[i] + (size_t)p * F, (size_t)c * F * sizeof(float),
+                                    F * sizeof(float), D, kind, st));
+    }
+    // bias table bp (T, 2cD) = pe[t].wp^T + [k_b | 0.. | v_b | 0..]: computed with the linear kernel
+    // (A = pe (T,F), W = wp, bias = flat bias (2cD)), staged through the workspace
+    int rc2 = arx_ws_reserve(h, (size_t)2 * c * D * sizeof(float) + 256);
+    if (rc2) return rc2;
+    float *flat = static_cast<float *>(h->ws);
+    ARX_CUDA(h, cudaMemsetAsync(flat, 0, (size_t)2 * c * D * sizeof(float), st));
+    ARX_CUDA(h, cudaMemcpyAsync(flat, w->k_b[i], D * sizeof(float), kind, st));
+    ARX_CUDA(h, cudaMemcpyAsync(flat + (size_t)c * D, w->v_b[i], D * sizeof(float), kind, st));
+    rc = arx_fp32_linear(h, tr.pe, F, tr.wp, F, flat, tr.bp, 2 * c * D, h->T, 2 * c * D, F, ARX_ACT_NONE, nullptr, 1, st);
+    if (rc) return rc;
+    // static softmax bound from the LayerNorm affine: |S| <= (max|g| sqrt(D) + ||b||_2)^2 / sqrt(D)
+    std::vector<float> g(D), b(D);
+    ARX_CUDA(h, cudaMemcpyAsync(g.data(), tr.ln_g, D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARX_CUDA(h, cudaMemcpyAsync(b.data(), tr.ln_b, D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARX_CUDA(h, cudaStreamSynchronize(st));
+    double gm = 0, bn = 0;
+    for (int d = 0; d < D; ++d) { gm = std::max(gm, (double)fabsf(g[d])); bn += (double)b[d] * b[d]; }
+    double r = gm * sqrt((double)D) + sqrt(bn);
+    tr.softmax_bound = (float)(r * r / sqrt((double)D));
+  }
+  if (h->cfg.has_discriminator) {
+    const int n2 = h->T * (h->T - 1) / 2;
+    UP(h->dr_w, w->dr_w, (size_t)h->T * h->D); UP(h->dr_b, w->dr_b, h->T);
+    UP(h->d1_w, w->d1_w, (size_t)256 * n2 * h->T); UP(h->d1_b, w->d1_b, 256);
+    UP(h->d2_w, w->d2_w, 64 * 256); UP(h->d2_b, w->d2_b, 64);
+    UP(h->d3_w, w->d3_w, 64); UP(h->d3_b, w->d3_b, 1);
+  }
+#undef UP
+  ARX_CUDA(h, cudaStreamSynchronize(st));
+  h->weights_loaded = true;
+  free_support(h);   // support operands depend on the weights
+  return ARX_OK;
+}
+
+int arx_tuple_count(const arx_handle *h, int32_t ti) {
+  if (!h || ti < 0 || ti >= h->cfg.n_transformers) return ARX_ERR_INVALID;
+  return h->tr[ti].N;
+}
+
+int arx_tuple_table(arx_handle *h, int32_t ti, int32_t *out_dev, void *stream) {
+  if (!h || !out_dev || ti < 0 || ti >= h->cfg.n_transformers) return arx_fail(h, ARX_ERR_INVALID, "tuple_table: bad argument");
+  const ArxTransformer &tr = h->tr[ti];
+  // rebuilt on device on every call (it is the kernel under test), not copied from the cached table
+  return arx_build_tuple_table(h, h->T, tr.c, tr.N, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int arx_embed(arx_handle *h, const float *frames_dev, int64_t n_frames, float *feats_dev, void *stream) {
+  if (!h || !frames_dev || !feats_dev || n_frames < 0) return arx_fail(h, ARX_ERR_INVALID, "embed: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "embed: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunk = 1 << 16;
+  int rc = arx_ws_reserve(h, (size_t)chunk * h->H * sizeof(float) + 256);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n_frames; r0 += chunk) {
+    int64_t r = std::min(chunk, n_frames - r0);
+    rc = embed_frames(h, frames_dev + r0 * h->J3, r, static_cast<float *>(h->ws), feats_dev + r0 * h->F, st);
+    if (rc) return rc;
+  }
+  return ARX_OK;
+}
+
+int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way, void *stream) {
+  if (!h || !feats_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (way > h->way_cap) {
+    ARX_CUDA(h, cudaStreamSynchronize(st));
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    free_support(h);
+    int rc;
+    for (int i = 0; i < h->cfg.n_transformers; ++i) {
+      if ((rc = dev_alloc(h, &h->tr[i].ks, (size_t)way * h->tr[i].N * h->D))) return rc;
+      if ((rc = dev_alloc(h, &h->tr[i].vs, (size_t)way * h->tr[i].N * h->D))) return rc;
+    }
+    if ((rc = dev_alloc(h, &h->ss_feat, (size_t)way * h->T * h->F))) return rc;
+    h->way_cap = way;
+  }
+  ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, feats_dev, (size_t)way * h->T * h->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < h->cfg.n_transformers; ++i) {
+    ArxTransformer &tr = h->tr[i];
+    size_t gbytes = (size_t)way * h->T * 2 * tr.c * h->D * sizeof(float) + 256;
+    int rc = arx_ws_reserve(h, gbytes);
+    if (rc) return rc;
+    float *G = static_cast<float *>(h->ws);
+    if ((rc = project_frames(h, tr, h->ss_feat, (int64_t)way * h->T, G, st))) return rc;
+    if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
+  }
+  h->way = way;
+  return ARX_OK;
+}
+
+int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, void *stream) {
+  if (!h || !poses_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *feats = nullptr;
+  ARX_CUDA(h, cudaMalloc(&feats, (size_t)way * h->T * h->F * sizeof(float)));
+  int rc = arx_embed(h, poses_dev, (int64_t)way * h->T, feats, st);
+  if (rc == ARX_OK) rc = arx_set_support_features(h, feats, way, st);
+  cudaStreamSynchronize(st);
+  cudaFree(feats);
+  return rc;
+}
+
+int arx_get_support_features(arx_handle *h, float *feats_dev, void *stream) {
+  if (!h || !feats_dev) return arx_fail(h, ARX_ERR_INVALID, "get_support_features: bad argument");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "get_support_features: no support set");
+  ARX_CUDA(h, cudaMemcpyAsync(feats_dev, h->ss_feat, (size_t)h->way * h->T * h->F * sizeof(float), cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  return ARX_OK;
+}
+
+int arx_support_way(const arx_handle *h) { return h ? h->way : ARX_ERR_INVALID; }
+
+int64_t arx_support_blob_bytes(const arx_handle *h, int32_t way) {
+  if (!h || way < 1) return ARX_ERR_INVALID;
+  int64_t n = (int64_t)way * h->T * h->F;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) n += 2ll * way * h->tr[i].N * h->D;
+  return n * (int64_t)sizeof(float);
+}
+
+int arx_export_support(arx_handle *h, void *blob_dev, void *stream) {
+  if (!h || !blob_dev) return arx_fail(h, ARX_ERR_INVALID, "export_support: bad argument");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "export_support: no support set");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *p = static_cast<float *>(blob_dev);
+  size_t n = (size_t)h->way * h->T * h->F;
+  ARX_CUDA(h, cudaMemcpyAsync(p, h->ss_feat, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  p += n;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) {
+    n = (size_t)h->way * h->tr[i].N * h->D;
+    ARX_CUDA(h, cudaMemcpyAsync(p, h->tr[i].ks, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += n;
+    ARX_CUDA(h, cudaMemcpyAsync(p, h->tr[i].vs, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += n;
+  }
+  return ARX_OK;
+}
+
+int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *stream) {
+  if (!h || !blob_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "import_support: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "import_support: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (way > h->way_cap) {
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    free_support(h);
+    int rc;
+    for (int i = 0; i < h->cfg.n_transformers; ++i) {
+      if ((rc = dev_alloc(h, &h->tr[i].ks, (size_t)way * h->tr[i].N * h->D))) return rc;
+      if ((rc = dev_alloc(h, &h->tr[i].vs, (size_t)way * h->tr[i].N * h->D))) return rc;
+    }
+    if ((rc = dev_alloc(h, &h->ss_feat, (size_t)way * h->T * h->F))) return rc;
+    h->way_cap = way;
+  }
+  const float *p = static_cast<const float *>(blob_dev);
+  size_t n = (size_t)way * h->T * h->F;
+  ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  p += n;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) {
+    n = (size_t)way * h->tr[i].N * h->D;
+    ARX_CUDA(h, cudaMemcpyAsync(h->tr[i].ks, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += n;
+    ARX_CUDA(h, cudaMemcpyAsync(h->tr[i].vs, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += n;
+  }
+  h->way = way;
+  return ARX_OK;
+}
+
+static int prof_mark(arx_handle *h, int idx, cudaStream_t st) {
+  if (!h->prof_on) return ARX_OK;
+  if (idx == 0) {
+    if (h->prof_used + ARX_N_STAGES + 1 > h->prof_events.size()) {
+      for (int i = 0; i < ARX_N_STAGES + 1; ++i) {
+        cudaEvent_t e;
+        ARX_CUDA(h, cudaEventCreate(&e));
+        h->prof_events.push_back(e);
+      }
+    }
+    h->prof_used += ARX_N_STAGES + 1;
+  }
+  ARX_CUDA(h, cudaEventRecord(h->prof_events[h->prof_used - (ARX_N_STAGES + 1) + idx], st));
+  return ARX_OK;
+}
+
+static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
+                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st) {
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score: weights not loaded");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score: support set not set");
+  if (n_windows == 0) return ARX_OK;
+  const ArxTransformer &tr = h->tr[ti];
+  const bool from_frames = query_dev != nullptr;
+  const bool disc = is_true_dev != nullptr;
+  if (disc && (!h->cfg.has_discriminator || ti != 0 || tr.c != 2))
+    return arx_fail(h, ARX_ERR_INVALID, "score: the discriminator is sized for pair tuples of transformers[0] (model.py:283-285)");
+  const int way = h->way;
+  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows);
+  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr);
+  size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
+  int rc = arx_ws_reserve(h, sz.bytes + extra);
+  if (rc) return rc;
+  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws);
+  int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
+  h->last_path = 1;
+  for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
+    const int64_t n = std::min(chunk, n_windows - b0);
+    const float *FE;
+    if ((rc = prof_mark(h, 0, st))) return rc;
+    if (from_frames) {
+      if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, n * h->T, w.H1, w.FE, st))) return rc;
+      FE = w.FE;
+    } else {
+      FE = qfeats_dev + b0 * h->T * h->F;
+    }
+    if ((rc = prof_mark(h, 1, st))) return rc;
+    if ((rc = project_frames(h, tr, FE, n * h->T, w.G, st))) return rc;
+    if ((rc = prof_mark(h, 2, st))) return rc;
+    if ((rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
+    if ((rc = prof_mark(h, 3, st))) return rc;
+    int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
+    const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
+    if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
+                                 probs ? probs + b0 * way * NN : nullptr, protos ? protos + b0 * way * ND : nullptr, st)))
+      return rc;
+    if ((rc = prof_mark(h, 4, st))) return rc;
+    if (disc) {
+      const int K1 = tr.N * h->T;
+      if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+      if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+      if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
+    }
+    if ((rc = prof_mark(h, 5, st))) return rc;
+  }
+  return ARX_OK;
+}
+
+int arx_score(arx_handle *h, const float *query_dev, int64_t n_windows, float *logits_dev, float *is_true_dev, int32_t *chosen_dev,
+              void *stream) {
+  if (!h || !query_dev || !logits_dev || n_windows < 0) return arx_fail(h, ARX_ERR_INVALID, "score: bad argument");
+  if (!h->cfg.has_discriminator) is_true_dev = nullptr;
+  return score_impl(h, 0, query_dev, nullptr, n_windows, logits_dev, is_true_dev, chosen_dev, nullptr, nullptr,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int arx_score_features(arx_handle *h, int32_t ti, const float *qfeats_dev, int64_t n_windows, float *logits_dev, void *stream) {
+  if (!h || !qfeats_dev || !logits_dev || n_windows < 0 || ti < 0 || ti >= h->cfg.n_transformers)
+    return arx_fail(h, ARX_ERR_INVALID, "score_features: bad argument");
+  return score_impl(h, ti, nullptr, qfeats_dev, n_windows, logits_dev, nullptr, nullptr, nullptr, nullptr,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int arx_debug_attention(arx_handle *h, const float *query_dev, int64_t n_windows, float *probs_dev, float *prototypes_dev, void *stream) {
+  if (!h || !query_dev || n_windows < 0) return arx_fail(h, ARX_ERR_INVALID, "debug_attention: bad argument");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "debug_attention: support set not set");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float *logits = nullptr;
+  ARX_CUDA(h, cudaMalloc(&logits, (size_t)std::max<int64_t>(1, n_windows) * h->way * sizeof(float)));
+  int rc = score_impl(h, 0, query_dev, nullptr, n_windows, logits, nullptr, nullptr, probs_dev, prototypes_dev, st);
+  cudaStreamSynchronize(st);
+  cudaFree(logits);
+  return rc;
+}
+
+int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, float *logits_host, float *is_true_host,
+                   int32_t *chosen_host) {
+  if (!h || !query_host || !logits_host || n_windows < 0) return arx_fail(h, ARX_ERR_INVALID, "score_host: bad argument");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score_host: support set not set");
+  if (n_windows == 0) return ARX_OK;
+  const bool disc = h->cfg.has_discriminator && is_true_host;
+  const int way = h->way;
+  const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);
+  const size_t out_per = (size_t)(way + 2) * sizeof(float);   // logits | is_true | chosen
+  const int64_t stage = std::min<int64_t>(n_windows, h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096);
+  if ((size_t)stage > h->stage_windows || way != h->stage_way) {
+    // (re)allocate staging sized for `stage` windows at the current way
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]);
+      h->dev_in[i] = h->dev_out[i] = nullptr;
+      ARX_CUDA(h, cudaMalloc(&h->dev_in[i], stage * in_per));
+      ARX_CUDA(h, cudaMalloc(&h->dev_out[i], stage * out_per));
+      if (!h->own_stream[i]) ARX_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream[i], cudaStreamNonBlocking));
+      if (!h->stage_ev[i]) ARX_CUDA(h, cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+    }
+    h->stage_windows = (size_t)stage;
+    h->stage_way = way;
+  }
+  // Two streams ping-pong over chunks: chunk i's H2D + compute + D2H run on stream i&1; the shared
+  // workspace serialises the compute of consecutive chunks through stage_ev.
+  int64_t i = 0;
+  for (int64_t b0 = 0; b0 < n_windows; b0 += stage, ++i) {
+    const int s = (int)(i & 1);
+    const int64_t n = std::min(stage, n_windows - b0);
+    cudaStream_t st = h->own_stream[s];
+    float *din = static_cast<float *>(h->dev_in[s]);
+    float *dlog = static_cast<float *>(h->dev_out[s]);
+    float *dist = dlog + (size_t)stage * way;
+    int32_t *dch = reinterpret_cast<int32_t *>(dist + stage);
+    ARX_CUDA(h, cudaMemcpyAsync(din, query_host + b0 * h->T * h->J3, n * in_per, cudaMemcpyHostToDevice, st));
+    if (i > 0) ARX_CUDA(h, cudaStreamWaitEvent(st, h->stage_ev[s ^ 1], 0));   // previous chunk done with the workspace
+    int rc = score_impl(h, 0, din, nullptr, n, dlog, disc ? dist : nullptr, dch, nullptr, nullptr, st);
+    if (rc) return rc;
+    ARX_CUDA(h, cudaEventRecord(h->stage_ev[s], st));
+    ARX_CUDA(h, cudaMemcpyAsync(logits_host + b0 * way, dlog, (size_t)n * way * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (disc) ARX_CUDA(h, cudaMemcpyAsync(is_true_host + b0, dist, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (chosen_host) ARX_CUDA(h, cudaMemcpyAsync(chosen_host + b0, dch, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  ARX_CUDA(h, cudaStreamSynchronize(h->own_stream[0]));
+  ARX_CUDA(h, cudaStreamSynchronize(h->own_stream[1]));
+  return ARX_OK;
+}
+
+int arx_decode_heatmaps(arx_handle *h, const float *logits_dev, int64_t n_frames, const float *expand_dev, int32_t n_out,
+                        const float *new_K_host9, const float *homo_inv_host9, float *poses_dev, uint8_t *valid_dev, void *stream) {
+  if (!h || !logits_dev || !expand_dev || !new_K_host9 || !homo_inv_host9 || !poses_dev || !valid_dev || n_frames < 0 || n_out < 1)
+    return arx_fail(h, ARX_ERR_INVALID, "decode_heatmaps: bad argument");
+  return arx_decode_launch(h, logits_dev, n_frames, expand_dev, n_out, new_K_host9, homo_inv_host9, poses_dev, valid_dev,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int arx_profile_enable(arx_handle *h, int32_t on) {
+  if (!h) return ARX_ERR_INVALID;
+  h->prof_on = on != 0;
+  return ARX_OK;
+}
+
+int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset) {
+  if (!h) return ARX_ERR_INVALID;
+  const size_t per = ARX_N_STAGES + 1;
+  for (size_t c = 0; c + per <= h->prof_used; c += per) {
+    ARX_CUDA(h, cudaEventSynchronize(h->prof_events[c + ARX_N_STAGES]));
+    for (int s = 0; s < ARX_N_STAGES; ++s) {
+      float t = 0.f;
+      ARX_CUDA(h, cudaEventElapsedTime(&t, h->prof_events[c + s], h->prof_events[c + s + 1]));
+      h->prof_ms[s] += t;
+    }
+    h->prof_chunks++;
+  }
+  h->prof_used = 0;
+  if (ms) for (int s = 0; s < ARX_N_STAGES; ++s) ms[s] = h->prof_ms[s];
+  if (chunks) *chunks = h->prof_chunks;
+  if (reset) {
+    for (int s = 0; s < ARX_N_STAGES; ++s) h->prof_ms[s] = 0;
+    h->prof_chunks = 0;
+  }
+  return ARX_OK;
+}
+
+int64_t arx_launch_count(const arx_handle *h) { return h ? h->launches : 0; }
+int arx_last_path(const arx_handle *h) { return h ? h->last_path : 0; }
+
+}  // extern "C"

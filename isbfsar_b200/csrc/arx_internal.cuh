@@ -1,0 +1,102 @@
+// Internal declarations shared by the translation units of libarx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/arx.h"
+
+#define ARX_SOFTMAX_LOG2E 1.4426950408889634f
+
+struct ArxTransformer {
+  int c = 0;            // tuple cardinality
+  int N = 0;            // C(T,c)
+  int Npad = 0;         // N rounded up to 128 (tcgen05 tile rows)
+  float *pe = nullptr;      // (T,F) slice of the reference buffer
+  float *wp = nullptr;      // (2cD, F): K parts then V parts of k_linear/v_linear (model.py:41-44)
+  float *bp = nullptr;      // (2cD): k bias on K part 0, v bias on V part 0, zero elsewhere
+  float *ln_g = nullptr, *ln_b = nullptr;
+  int32_t *tuples = nullptr; // (N,c) int32, built on device
+  // support operands, fp32 generic path: (W,N,D) each
+  float *ks = nullptr, *vs = nullptr;
+  // support operands, tcgen05 path: fp16 UMMA smem images, see arx_tc.cu
+  __half *ks_img = nullptr, *vs_img = nullptr;
+  float softmax_bound = 0.f; // static |S| bound from LayerNorm affine
+};
+
+struct arx_handle {
+  arx_config cfg{};
+  int device = 0;
+  int sm_count = 0;
+  int T = 0, J3 = 0, H = 0, F = 0, D = 0;
+  bool weights_loaded = false;
+  // MLP (model.py:164-180)
+  float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;
+  ArxTransformer tr[ARX_MAX_TRANSFORMERS];
+  // discriminator (model.py:183-204)
+  float *dr_w = nullptr, *dr_b = nullptr, *d1_w = nullptr, *d1_b = nullptr;
+  float *d2_w = nullptr, *d2_b = nullptr, *d3_w = nullptr, *d3_b = nullptr;
+  // support set
+  int way = 0;
+  int way_cap = 0;
+  float *ss_feat = nullptr;   // (W,T,F)
+  // workspace (grown on demand)
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  // pinned staging for arx_score_host
+  void *pin_in[2] = {nullptr, nullptr};
+  void *pin_out[2] = {nullptr, nullptr};
+  void *dev_in[2] = {nullptr, nullptr};
+  void *dev_out[2] = {nullptr, nullptr};
+  size_t stage_windows = 0;
+  int stage_way = 0;
+  cudaStream_t own_stream[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  int64_t launches = 0;
+  // stage timers (arx_profile_*)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;   // ARX_N_STAGES+1 events per recorded chunk
+  size_t prof_used = 0;
+  double prof_ms[ARX_N_STAGES] = {0, 0, 0, 0, 0};
+  int64_t prof_chunks = 0;
+  int last_path = 0;
+  std::string err;
+};
+
+int arx_fail(arx_handle *h, int code, const char *fmt, ...);
+#define ARX_CUDA(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return arx_fail((h), ARX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+  } while (0)
+#define ARX_LAUNCH_CHECK(h)                                                            \
+  do {                                                                                 \
+    (h)->launches++;                                                                   \
+    ARX_CUDA((h), cudaGetLastError());                                                 \
+  } while (0)
+
+int arx_ws_reserve(arx_handle *h, size_t bytes);
+
+// ---- fp32 generic kernels (arx_fp32.cu) ------------------------------------------
+enum ArxAct { ARX_ACT_NONE = 0, ARX_ACT_RELU = 1, ARX_ACT_SIGMOID = 2 };
+// C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ pe[(row % peT), N] after act when pe != nullptr)
+int arx_fp32_linear(arx_handle *h, const float *A, int lda, const float *W, int ldw, const float *bias,
+                    float *C, int ldc, int64_t M, int N, int K, int act, const float *pe, int peT,
+                    cudaStream_t st);
+// tuple K (LayerNorm-ed) and V from per-frame projections G (rows = n_seq*T, 2cD)
+int arx_fp32_build_tuples(arx_handle *h, const ArxTransformer &tr, const float *G, int64_t n_seq,
+                          float *K, float *V, cudaStream_t st);
+// attention + distances (two passes), see arx_fp32.cu
+int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq, const float *Vq,
+                       int64_t n_win, int way, float *Z, float *partial, float *logits, int32_t *chosen,
+                       float *y /* (n_win, N*T) or null */, float *probs, float *protos, cudaStream_t st);
+
+// ---- tuple table (arx_tuples.cu) -------------------------------------------------
+int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);
+
+// ---- decode (arx_decode.cu) ------------------------------------------------------
+int arx_decode_launch(arx_handle *h, const float *logits, int64_t n_frames, const float *expand, int n_out,
+                      const float *K9, const float *R9, float *poses, uint8_t *valid, cudaStream_t st);

@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python API) against the CPU oracle
+and the golden vectors frozen from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): tuple indices bit-exact; logits and is_true within 1e-3 relative;
+identical argmax and accept/reject on >= 99.9 % of windows.  The fp32 CUDA-core path is held to 5e-5."""
+import os
+from itertools import combinations
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.synth import Cfg, make_episode, make_state_dict, make_heatmaps
+from oracle.trx_oracle import TrxOracle
+from tests.util import Args, make_model, rel_err, torch_sd
+
+pytestmark = pytest.mark.gpu
+
+TOL_TC = 1e-3       # stated tolerance (fp16 operands, fp32 accumulate)
+TOL_FP32 = 5e-5     # fp32 path: summation-order noise only
+
+CASES = [
+    ("cfg1_w5_t16_structured", Cfg()),
+    ("cfg1_w5_t16_iid", Cfg()),
+    ("cfg1_w5_t16_affine", Cfg()),
+    ("w3_t16_structured", Cfg()),
+    ("cfg3_w60_t16", Cfg(way=60)),
+    ("cfg4_w20_t32_pairs", Cfg(way=20, seq_len=32, temp_set=[2, 3])),
+]
+PATHS = [1, 0]      # 1 = fp32 kernels forced, 0 = auto (tcgen05 where available)
+
+
+def tol_for(model):
+    return TOL_FP32 if model.last_path() == 1 else TOL_TC
+
+
+@pytest.mark.parametrize("T,c", [(4, 2), (8, 2), (16, 2), (32, 2), (8, 3), (16, 3), (32, 3)])
+def test_tuple_table_bit_exact(T, c):
+    m, _ = make_model(Cfg(seq_len=T, temp_set=[c], model="DISC" if c == 2 else "NONE"))
+    tab = m.tuple_table(0).cpu().numpy()
+    ref = np.array(list(combinations(range(T), c)), dtype=np.int32)
+    assert tab.dtype == np.int32 and np.array_equal(tab, ref)
+    assert [t.tolist() for t in m.transformers[0].tuples] == ref.tolist()
+    assert m.transformers[0].tuples[0].dtype == torch.int64
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("name,cfg", CASES)
+def test_scores_match_reference_golden(golden_dir, name, cfg, path):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    way, T, B, wseed, iseed, affine = [int(x) for x in g["meta"][:6]]
+    m, sd = make_model(cfg, wseed, affine=bool(affine), force_path=path)
+    support, labels, query, planted = make_episode(cfg, B, iseed, str(g["kind"]), way=way)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    tol = tol_for(m)
+    logits, is_true = logits.cpu().numpy(), is_true.cpu().numpy()
+    assert rel_err(logits, g["logits"]).max() < tol
+    assert rel_err(is_true, g["is_true"]).max() < tol
+    if str(g["kind"]) == "structured":
+        assert np.array_equal(logits.argmax(1), g["logits"].argmax(1))
+    assert np.array_equal(is_true > 0.5, g["is_true"] > 0.5)
+    np.testing.assert_allclose(m.support_features().cpu().numpy()[:2], g["support_features"], rtol=tol, atol=1e-6)
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("kind", ["structured", "iid"])
+def test_scores_match_oracle_b512(kind, path):
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0, force_path=path)
+    support, labels, query, planted = make_episode(cfg, 512, 11, kind)
+    o = TrxOracle(cfg, sd)
+    lo, it = o.score(support, labels, query)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true, chosen = m.score(torch.from_numpy(query).cuda(), want_chosen=True)
+    tol = tol_for(m)
+    logits, is_true = logits.cpu().numpy(), is_true.cpu().numpy()
+    assert rel_err(logits, lo).max() < tol
+    assert rel_err(is_true, it).max() < tol
+    assert np.array_equal(chosen.cpu().numpy(), logits.argmax(1))
+    if kind == "structured":
+        assert (logits.argmax(1) == lo.argmax(1)).mean() >= 0.999
+        assert (logits.argmax(1) == planted).all()
+    else:   # ill-posed margins: compare argmax only where the reference margin exceeds 2*tol
+        srt = np.sort(lo, 1)
+        ok = (srt[:, -1] - srt[:, -2]) / np.abs(srt[:, -1]) > 2 * tol
+        assert (logits.argmax(1)[ok] == lo.argmax(1)[ok]).all()
+    assert ((is_true > 0.5) == (it > 0.5)).mean() >= 0.999
+
+
+def test_forward_reference_api():
+    """forward(ss_data, ss_labels, query_data, ss_features) -- return dict, label order, cached/uncached."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    o = TrxOracle(cfg, sd)
+    support, labels, query, _ = make_episode(cfg, 8, 21, "structured")
+    S, Q = torch.from_numpy(support).cuda(), torch.from_numpy(query).cuda()
+    out = m({"sk": S}, torch.from_numpy(labels).cuda(), {"sk": Q})
+    assert set(out) == {"logits", "is_true", "prototypes", "support_features"}
+    assert out["logits"].shape == (8, 5) and out["is_true"].shape == (8, 1)
+    assert out["support_features"].shape == (8, 5, 16, 256)
+    ref = o.forward({"sk": np.repeat(support, 8, 0)}, labels, {"sk": query}, want=("prototypes",))
+    tol = tol_for(m)
+    assert rel_err(out["logits"].cpu(), ref["logits"]).max() < tol
+    assert rel_err(out["is_true"].cpu(), ref["is_true"]).max() < tol
+    np.testing.assert_allclose(out["support_features"][0].cpu().numpy(), ref["support_features"][0].numpy(), rtol=tol, atol=1e-6)
+    # prototypes: list of W (b,1,N,D) (fp32 debug kernels)
+    protos = out["prototypes"]
+    assert len(protos) == 5 and protos[0].shape == (8, 1, 120, 128)
+    np.testing.assert_allclose(protos[3].cpu().numpy(), ref["prototypes"][3].numpy(), rtol=1e-3, atol=2e-5)
+    # cached path: ss_features expanded over the batch (ar.py:56-61 / SURVEY 3.3)
+    ssf = out["support_features"][:1]
+    out2 = m(None, torch.from_numpy(labels).cuda(), {"sk": Q}, ss_features=ssf.expand(8, -1, -1, -1))
+    assert rel_err(out2["logits"].cpu(), out["logits"].cpu()).max() < 1e-5
+    # label permutation: logits column k belongs to class ss_labels[0][k]
+    perm = np.array([[3, 1, 4, 0, 2]], dtype=np.int32)
+    out3 = m({"sk": S}, torch.from_numpy(perm).cuda(), {"sk": Q})
+    assert rel_err(out3["logits"].cpu(), out["logits"].cpu()[:, perm[0]]).max() < 1e-5
+    # a subset of the classes (ar.py:51: labels = range(n) with a zero-padded feature stack)
+    sub = np.array([[0, 1, 2]], dtype=np.int32)
+    out4 = m(None, torch.from_numpy(sub).cuda(), {"sk": Q}, ss_features=ssf)
+    assert out4["logits"].shape == (8, 3)
+    ref4 = o.forward(None, sub, {"sk": query}, ss_features=ref["support_features"])
+    assert rel_err(out4["logits"].cpu(), ref4["logits"]).max() < tol
+
+
+def test_forward_per_episode_support():
+    """Training/eval call shape (train.py:110-120): every batch row has its own support set."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    o = TrxOracle(cfg, sd)
+    rng = np.random.default_rng(5)
+    b = 4
+    support = (0.17 * rng.standard_normal((b, 5, 16, 90))).astype(np.float32)
+    query = (support[np.arange(b), rng.integers(0, 5, b)] + 0.05 * rng.standard_normal((b, 16, 90))).astype(np.float32)
+    labels = np.tile(np.arange(5, dtype=np.int32), (b, 1))
+    out = m({"sk": torch.from_numpy(support).cuda()}, torch.from_numpy(labels).cuda(), {"sk": torch.from_numpy(query).cuda()})
+    ref = o.forward({"sk": support}, labels, {"sk": query})
+    tol = tol_for(m)
+    assert rel_err(out["logits"].cpu(), ref["logits"]).max() < tol
+    assert rel_err(out["is_true"].cpu(), ref["is_true"]).max() < tol
+    assert out["support_features"].shape == (b, 5, 16, 256)
+
+
+@pytest.mark.parametrize("name,cfg,way_run", [("w5_t16_triples", Cfg(way=5, seq_len=16, temp_set=[2, 3]), 5),
+                                              ("cfg4_w20_t32_triples", Cfg(way=20, seq_len=32, temp_set=[2, 3]), 20)])
+def test_triple_transformer_logits(golden_dir, name, cfg, way_run):
+    """Cardinality-3 transformer validated against ref.transformers[1](...)['logits']."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    way, T, B, wseed, iseed, ti = [int(x) for x in g["meta"][:6]]
+    m, sd = make_model(cfg, wseed)
+    support, labels, query, _ = make_episode(cfg, B, iseed, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    qf = m.embed(torch.from_numpy(query).cuda())
+    logits = m.score_features(ti, qf).cpu().numpy()
+    assert rel_err(logits, g["logits"]).max() < tol_for(m)
+    assert np.array_equal(m.tuple_table(ti).cpu().numpy(), g["tuples"].astype(np.int32))
+
+
+def test_action_recognizer_stream(golden_dir):
+    from isbfsar_b200 import ActionRecognizer
+    g = np.load(os.path.join(golden_dir, "ar_stream.npz"))
+    cfg = Cfg()
+    ar = ActionRecognizer(Args(cfg), state_dict=torch_sd(make_state_dict(cfg, 0)))
+    rng = np.random.default_rng(7)
+    poses = (0.17 * rng.standard_normal((3, 16, 90))).astype(np.float32)
+    frames = (0.17 * rng.standard_normal((23, 90))).astype(np.float32)
+    frames[5:21] = poses[1] + 0.05 * rng.standard_normal((16, 90)).astype(np.float32)
+    assert ar.inference(None) == ({}, 0, {})
+    assert ar.inference({"sk": frames[0]}) == ({}, 0, {})
+    for i, n in enumerate(["wave", "clap", "kick"]):
+        ar.train({"flag": n, "data": {"poses": poses[i]}, "requires_focus": bool(i % 2)})
+    probs, os_, empties = [], [], 0
+    for f in range(20):
+        res, o, rf = ar.inference({"sk": frames[f]})
+        if len(res) == 0:
+            empties += 1
+            continue
+        assert list(res.keys()) == ["wave", "clap", "kick"] and rf == {"wave": False, "clap": True, "kick": False}
+        assert isinstance(o, np.ndarray) and o.shape == (1,)
+        probs.append([res[k] for k in res])
+        os_.append(float(o[0]))
+    assert empties == int(g["empties"])
+    assert rel_err(np.array(probs), g["probs"]).max() < 2e-3      # softmax of logits within 1e-3 relative
+    assert rel_err(np.array(os_), g["open_set"]).max() < 1e-3
+    assert np.array_equal(np.argmax(probs, 1), np.argmax(g["probs"], 1))
+    feats = torch.stack([ar.support_set[k]["features"] for k in ["wave", "clap", "kick"]]).cpu().numpy()
+    np.testing.assert_allclose(feats[:, :2], g["features"], rtol=1e-3, atol=1e-6)
+    assert ar.remove("clap") and not ar.remove("nope")
+    probs2 = []
+    for f in range(20, 23):
+        res, o, rf = ar.inference({"sk": frames[f]})
+        probs2.append([res[k] for k in ["wave", "kick"]])
+    assert rel_err(np.array(probs2), g["probs_after_remove"]).max() < 2e-3
+
+
+def test_decode_heatmaps(golden_dir):
+    from isbfsar_b200 import HeatmapDecoder
+    g = np.load(os.path.join(golden_dir, "decode_64.npz"))
+    m, _ = make_model(Cfg(), 0)
+    dec = HeatmapDecoder(m, g["expand30"], None, g["new_K"], g["homo_inv"])
+    hm = make_heatmaps(64, seed=2)
+    poses, valid = dec.decode(torch.from_numpy(hm).cuda())
+    assert valid.all() and np.array_equal(valid.cpu().numpy(), g["valid"])
+    # fp32 soft-argmax vs the reference's float64 tail: 1e-4 of the pose scale
+    ref = g["poses"]
+    assert np.abs(poses.cpu().numpy() - ref).max() < 1e-4 * np.abs(ref).max()
+    assert (poses[:, :3] == 0).all()           # root joint exactly zero (main.py:103)
+    # frames with fewer than 1/4 of the joints inside the FOV are dropped (hpe.py:152-153)
+    bad = torch.zeros((3, 8, 8, 288), device="cuda")
+    bad[:, 0, 0, :] = 30.0                      # every joint piles up in the corner -> outside [18,238]
+    p, v = dec.decode(bad)
+    assert not v.any() and (p == 0).all()
+
+
+def test_score_host_matches_device_and_chunking():
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0, max_chunk=96)       # ragged chunks: 300 = 3*96 + 12
+    support, labels, query, _ = make_episode(cfg, 300, 31, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    a, b = m.score(torch.from_numpy(query).cuda())
+    hq = torch.from_numpy(query).pin_memory()
+    ha, hb = m.score_host(hq)
+    assert torch.equal(a.cpu(), ha) and torch.equal(b.cpu(), hb)
+    m2, _ = make_model(cfg, 0)
+    m2.set_support(poses=torch.from_numpy(support[0]).cuda())
+    a2, b2 = m2.score(torch.from_numpy(query).cuda())
+    assert torch.equal(a2, a) and torch.equal(b2, b)                 # results independent of chunking
+    # empty batch
+    e, f = m.score(torch.zeros((0, 16, 90)).cuda())
+    assert e.shape == (0, 5) and f.shape == (0, 1)
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE cfg2 (4096 windows, 5-way): size-independent properties instead of the slow oracle."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, planted = make_episode(cfg, 4096, 41, "structured")
+    S, Q = torch.from_numpy(support[0]).cuda(), torch.from_numpy(query).cuda()
+    m.set_support(poses=S)
+    logits, is_true = m.score(Q)
+    assert torch.isfinite(logits).all() and (logits < 0).all() and ((is_true > 0) & (is_true < 1)).all()
+    assert (logits.argmax(1).cpu().numpy() == planted).all()
+    # windows are independent: a permuted batch gives permuted rows, bit-identical
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(0)).cuda()
+    l2, t2 = m.score(Q[perm])
+    assert torch.equal(l2, logits[perm]) and torch.equal(t2, is_true[perm])
+    # class permutation of the support set permutes the columns
+    cp = torch.tensor([2, 0, 4, 1, 3]).cuda()
+    m.set_support(poses=S[cp])
+    l3, t3 = m.score(Q)
+    assert rel_err(l3.cpu(), logits[:, cp].cpu()).max() < 1e-5
+    assert rel_err(t3.cpu(), is_true.cpu()).max() < 1e-5
+    # a query identical to a support class: that class wins
+    m.set_support(poses=S)
+    l4, _ = m.score(S)
+    assert (l4.argmax(1).cpu() == torch.arange(5)).all()
+    # subset oracle check on 64 of the windows
+    o = TrxOracle(cfg, sd)
+    lo, it = o.score(support, labels, query[:64])
+    assert rel_err(logits[:64].cpu(), lo).max() < tol_for(m)
+    assert rel_err(is_true[:64].cpu(), it).max() < tol_for(m)
+
+
+def test_errors_are_loud():
+    cfg = Cfg()
+    m, _ = make_model(cfg, 0)
+    with pytest.raises(RuntimeError):
+        m.score(torch.zeros((1, 16, 90)).cuda())            # support not set
+    from isbfsar_b200 import TRXOS
+    cpu_model = TRXOS(Args(cfg))
+    with pytest.raises(RuntimeError):
+        cpu_model({"sk": torch.zeros(1, 5, 16, 90)}, torch.arange(5)[None], {"sk": torch.zeros(1, 16, 90)})
