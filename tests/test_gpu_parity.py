@@ -98,7 +98,7 @@ def test_forward_reference_api():
     out = m({"sk": S}, torch.from_numpy(labels).cuda(), {"sk": Q})
     assert set(out) == {"logits", "is_true", "prototypes", "support_features"}
     assert out["logits"].shape == (8, 5) and out["is_true"].shape == (8, 1)
-    assert out["support_features"].shape == (8, 5, 16, 256)
+    assert out["support_features"].shape == (1, 5, 16, 256)      # batch dim of the support given (model.py:315-317)
     ref = o.forward({"sk": np.repeat(support, 8, 0)}, labels, {"sk": query}, want=("prototypes",))
     tol = tol_for(m)
     assert rel_err(out["logits"].cpu(), ref["logits"]).max() < tol
