@@ -155,6 +155,10 @@ ARX_API int arx_decode_heatmaps(arx_handle *h, const float *logits_dev, int64_t 
 ARX_API int arx_profile_enable(arx_handle *h, int32_t on);
 ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset);
 
+/* Debug knobs for kernel bring-up and tests.  key 0: tcgen05 attention variant (bit 0 = K-major
+ * layout of the P operand instead of MN-major). */
+ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
+
 /* Introspection for tests/bench: kernel launches issued by this handle so far,
  * and which attention path the last arx_score used (1 = fp32, 2 = tcgen05). */
 ARX_API int64_t arx_launch_count(const arx_handle *h);

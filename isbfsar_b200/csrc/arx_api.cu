@@ -86,18 +86,21 @@ void free_support(arx_handle *h) {
 // per-window workspace of the fp32 path
 struct Fp32Ws {
   float *H1, *FE, *G, *Kq, *Vq, *Z, *partial, *y, *h1, *h2;
+  __half *kq_img;
   size_t bytes;
 };
-Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, void *base) {
+Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, void *base,
+                  bool tc = false, bool tuples32 = true) {
   Carver c(base);
   Fp32Ws w{};
-  const int nb = (tr.N + 63) / 64;
+  const int nb = tc ? 4 : (tr.N + 63) / 64;
+  w.kq_img = tc ? c.take<__half>(n * 128 * 128) : nullptr;
   w.H1 = from_frames ? c.take<float>(n * h->T * h->H) : nullptr;
   w.FE = from_frames ? c.take<float>(n * h->T * h->F) : nullptr;
   w.G = c.take<float>(n * h->T * 2 * tr.c * h->D);
-  w.Kq = c.take<float>(n * tr.N * h->D);
-  w.Vq = c.take<float>(n * tr.N * h->D);
-  w.Z = c.take<float>(n * way * tr.N * 2);
+  w.Kq = tuples32 ? c.take<float>(n * tr.N * h->D) : nullptr;
+  w.Vq = tuples32 ? c.take<float>(n * tr.N * h->D) : nullptr;
+  w.Z = tuples32 ? c.take<float>(n * way * tr.N * 2) : nullptr;
   w.partial = c.take<float>(n * way * nb);
   w.y = disc ? c.take<float>(n * tr.N * h->T) : nullptr;
   w.h1 = disc ? c.take<float>(n * 256) : nullptr;
@@ -106,8 +109,9 @@ Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, b
   return w;
 }
 
-int64_t pick_chunk(arx_handle *h, const ArxTransformer &tr, int way, bool from_frames, bool disc, int64_t n_total) {
-  Fp32Ws one = carve_fp32(h, tr, 1, way, from_frames, disc, nullptr);
+int64_t pick_chunk(arx_handle *h, const ArxTransformer &tr, int way, bool from_frames, bool disc, int64_t n_total, bool tc,
+                   bool tuples32) {
+  Fp32Ws one = carve_fp32(h, tr, 1, way, from_frames, disc, nullptr, tc, tuples32);
   int64_t cap = h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096;
   const size_t budget = (size_t)3 << 30;
   int64_t fit = (int64_t)(budget / one.bytes);
@@ -329,6 +333,7 @@ int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way,
     float *G = static_cast<float *>(h->ws);
     if ((rc = project_frames(h, tr, h->ss_feat, (int64_t)way * h->T, G, st))) return rc;
     if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
+    if (h->cfg.force_path != 1 && arx_tc_supported(h, tr) && (rc = arx_tc_prep_support(h, tr, way, st))) return rc;
   }
   h->way = way;
   return ARX_OK;
@@ -407,6 +412,8 @@ int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *s
     p += n;
     ARX_CUDA(h, cudaMemcpyAsync(h->tr[i].vs, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p += n;
+    int rc2;
+    if (h->cfg.force_path != 1 && arx_tc_supported(h, h->tr[i]) && (rc2 = arx_tc_prep_support(h, h->tr[i], way, st))) return rc2;
   }
   h->way = way;
   return ARX_OK;
@@ -439,14 +446,21 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   if (disc && (!h->cfg.has_discriminator || ti != 0 || tr.c != 2))
     return arx_fail(h, ARX_ERR_INVALID, "score: the discriminator is sized for pair tuples of transformers[0] (model.py:283-285)");
   const int way = h->way;
-  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows);
-  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr);
+  const bool debug_out = probs || protos;
+  bool use_tc = h->cfg.force_path != 1 && !debug_out && arx_tc_supported(h, tr) && tr.ks_img != nullptr;
+  if (h->cfg.force_path == 2 && !use_tc && !debug_out)
+    return arx_fail(h, ARX_ERR_INVALID, "score: force_path=2 but the tcgen05 path does not support this shape (N=%d, bound=%g)", tr.N,
+                    (double)tr.softmax_bound);
+  const bool mode0 = use_tc && h->T == 16 && tr.c == 2;
+  const bool tuples32 = !use_tc || disc || !mode0;    // fp32 tuple tensors: fp32 path, open-set head pass, generic epilogue
+  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32);
+  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32);
   size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
   int rc = arx_ws_reserve(h, sz.bytes + extra);
   if (rc) return rc;
-  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws);
+  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, use_tc, tuples32);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
-  h->last_path = 1;
+  h->last_path = use_tc ? 2 : 1;
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
     const int64_t n = std::min(chunk, n_windows - b0);
     const float *FE;
@@ -460,14 +474,23 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     if ((rc = prof_mark(h, 1, st))) return rc;
     if ((rc = project_frames(h, tr, FE, n * h->T, w.G, st))) return rc;
     if ((rc = prof_mark(h, 2, st))) return rc;
-    if ((rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
+    if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
+    if (use_tc && (rc = arx_tc_prep_query(h, tr, w.G, n, w.kq_img, st))) return rc;
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
-    if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
-                                 probs ? probs + b0 * way * NN : nullptr, protos ? protos + b0 * way * ND : nullptr, st)))
-      return rc;
-    if ((rc = prof_mark(h, 4, st))) return rc;
+    if (use_tc) {
+      if ((rc = arx_tc_attention(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, w.partial, logits_dev + b0 * way, ch,
+                                 h->tc_variant, st)))
+        return rc;
+      if ((rc = prof_mark(h, 4, st))) return rc;
+      if (disc && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
+    } else {
+      if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
+                                   probs ? probs + b0 * way * NN : nullptr, protos ? protos + b0 * way * ND : nullptr, st)))
+        return rc;
+      if ((rc = prof_mark(h, 4, st))) return rc;
+    }
     if (disc) {
       const int K1 = tr.N * h->T;
       if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
@@ -589,6 +612,12 @@ int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset) 
     h->prof_chunks = 0;
   }
   return ARX_OK;
+}
+
+int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
+  if (!h) return ARX_ERR_INVALID;
+  if (key == 0) { h->tc_variant = value; return ARX_OK; }
+  return arx_fail(h, ARX_ERR_INVALID, "debug_set: unknown key %d", key);
 }
 
 int64_t arx_launch_count(const arx_handle *h) { return h ? h->launches : 0; }

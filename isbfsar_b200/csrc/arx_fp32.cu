@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(256) k_build_tuples(const float *__restrict__ 
 // Pass A: per support tuple s of class c, online (max, sum) over ALL query tuples q of window b:
 //   M[s] = max_q S[q,s],  Z[s] = sum_q exp(S[q,s] - M[s]),  S = Kq.Ks^T / sqrt(D)     (model.py:101-109)
 __global__ void __launch_bounds__(256) k_colstats(const float *__restrict__ Kq, const float *__restrict__ Ks,
-                                                  float *__restrict__ Zo, int N, int D, int way, float scale) {
+                                                  float *__restrict__ Zo, int N, int D, int way, float scale,
+                                                  const int32_t *__restrict__ chosen) {
   __shared__ __align__(16) float As[TK][TM + TPAD];
   __shared__ __align__(16) float Bs[TK][TN + TPAD];
-  const int sb = blockIdx.x, c = blockIdx.y;
+  const int sb = blockIdx.x;
   const int64_t b = blockIdx.z;
+  const int c = chosen ? chosen[b] : blockIdx.y;
   const float *ks = Ks + (int64_t)c * N * D;
   const float *kq = Kq + b * (int64_t)N * D;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
@@ -347,7 +349,7 @@ int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq,
     int64_t nb_win = n_win - b0 < 65535 ? n_win - b0 : 65535;
     for (int c0 = 0; c0 < way; c0 += 65535) {  // way never exceeds this; kept for form
       dim3 gA(nb, way, (unsigned)nb_win);
-      k_colstats<<<gA, 256, 0, st>>>(Kq + b0 * N * D, tr.ks, Z + b0 * way * N * 2, N, D, way, scale);
+      k_colstats<<<gA, 256, 0, st>>>(Kq + b0 * N * D, tr.ks, Z + b0 * way * N * 2, N, D, way, scale, nullptr);
       ARX_LAUNCH_CHECK(h);
       k_attend<<<gA, 256, smem, st>>>(Kq + b0 * N * D, Vq + b0 * N * D, tr.ks, tr.vs, Z + b0 * way * N * 2,
                                       partial + b0 * way * nb, nullptr, nullptr, nullptr, nullptr, 0,
@@ -368,6 +370,27 @@ int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq,
                                       way, scale);
       ARX_LAUNCH_CHECK(h);
     }
+  }
+  return ARX_OK;
+}
+
+// Open-set head input for an already-known winning class (model.py:323-324,196): softmax statistics and the
+// attention pass for class chosen[b] only, emitting y = diff.Wdr^T + bdr.
+int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float *Kq, const float *Vq, int64_t n_win, int way,
+                           float *Z, const int32_t *chosen, float *y, cudaStream_t st) {
+  const int N = tr.N, D = h->D;
+  const int nb = (N + TM - 1) / TM;
+  const float scale = 1.0f / sqrtf((float)D);
+  const size_t smem = (size_t)(2 * TK * (TM + TPAD) + TM * PS_LD + TM * DF_LD) * sizeof(float);
+  ARX_CUDA(h, cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int64_t b0 = 0; b0 < n_win; b0 += 65535) {
+    int64_t nb_win = n_win - b0 < 65535 ? n_win - b0 : 65535;
+    dim3 g(nb, 1, (unsigned)nb_win);
+    k_colstats<<<g, 256, 0, st>>>(Kq + b0 * N * D, tr.ks, Z + b0 * way * N * 2, N, D, way, scale, chosen + b0);
+    ARX_LAUNCH_CHECK(h);
+    k_attend<<<g, 256, smem, st>>>(Kq + b0 * N * D, Vq + b0 * N * D, tr.ks, tr.vs, Z + b0 * way * N * 2, nullptr, chosen + b0,
+                                   y + b0 * N * h->T, h->dr_w, h->dr_b, h->T, nullptr, nullptr, N, D, way, scale);
+    ARX_LAUNCH_CHECK(h);
   }
   return ARX_OK;
 }

@@ -61,6 +61,7 @@ struct arx_handle {
   double prof_ms[ARX_N_STAGES] = {0, 0, 0, 0, 0};
   int64_t prof_chunks = 0;
   int last_path = 0;
+  int tc_variant = 0;   // debug: bit 0 selects the K-major P layout
   std::string err;
 };
 
@@ -93,6 +94,16 @@ int arx_fp32_build_tuples(arx_handle *h, const ArxTransformer &tr, const float *
 int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq, const float *Vq,
                        int64_t n_win, int way, float *Z, float *partial, float *logits, int32_t *chosen,
                        float *y /* (n_win, N*T) or null */, float *probs, float *protos, cudaStream_t st);
+
+int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float *Kq, const float *Vq, int64_t n_win, int way,
+                           float *Z, const int32_t *chosen, float *y, cudaStream_t st);
+
+// ---- tcgen05 kernels (arx_tc.cu) -------------------------------------------------
+bool arx_tc_supported(const arx_handle *h, const ArxTransformer &tr);
+int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
+int arx_tc_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, cudaStream_t st);
+int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

@@ -372,6 +372,9 @@ class TRXOS(nn.Module):
                    "arx_profile_read")
         return dict(zip(self.STAGES, list(ms))), int(n.value)
 
+    def debug_set(self, key, value):
+        _lib.check(_lib.load().arx_debug_set(self._ensure(), int(key), int(value)), self._h, "arx_debug_set")
+
     def launch_count(self):
         return int(_lib.load().arx_launch_count(self._h)) if self._h else 0
 
