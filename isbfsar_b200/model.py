@@ -303,6 +303,8 @@ class TRXOS(nn.Module):
         logits = torch.empty((B, way), dtype=torch.float32, device=dev)
         is_true = torch.empty((B, 1), dtype=torch.float32, device=dev) if self.model == "DISC" else None
         chosen = torch.empty((B,), dtype=torch.int32, device=dev) if want_chosen else None
+        if B == 0:
+            return (logits, is_true, chosen) if want_chosen else (logits, is_true)
         with torch.cuda.device(dev):
             _lib.check(lib.arx_score(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
                                      C.c_void_p(is_true.data_ptr()) if is_true is not None else None,
