@@ -213,6 +213,7 @@ void arx_destroy(arx_handle *h) {
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
+  cudaFree(h->wdr_img);
   cudaFree(h->ws);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
@@ -273,6 +274,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     UP(h->d1_w, w->d1_w, (size_t)256 * n2 * h->T); UP(h->d1_b, w->d1_b, 256);
     UP(h->d2_w, w->d2_w, 64 * 256); UP(h->d2_b, w->d2_b, 64);
     UP(h->d3_w, w->d3_w, 64); UP(h->d3_b, w->d3_b, 1);
+    if (h->cfg.force_path != 1 && (rc = arx_tc_prep_head_weights(h, st))) return rc;
   }
 #undef UP
   ARX_CUDA(h, cudaStreamSynchronize(st));
@@ -452,7 +454,8 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     return arx_fail(h, ARX_ERR_INVALID, "score: force_path=2 but the tcgen05 path does not support this shape (N=%d, bound=%g)", tr.N,
                     (double)tr.softmax_bound);
   const bool mode0 = use_tc && h->T == 16 && tr.c == 2;
-  const bool tuples32 = !use_tc || disc || !mode0;    // fp32 tuple tensors: fp32 path, open-set head pass, generic epilogue
+  const bool tc_head = use_tc && disc && arx_tc_head_supported(h, tr) && (h->tc_variant & 2) == 0;
+  const bool tuples32 = !use_tc || (disc && !tc_head) || !mode0;    // fp32 tuple tensors: fp32 path/head pass, generic epilogue
   const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32);
   Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32);
   size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
@@ -484,7 +487,8 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
                                  h->tc_variant, st)))
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
-      if (disc && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
+      if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, st))) return rc;
+      if (disc && !tc_head && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
     } else {
       if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
                                    probs ? probs + b0 * way * NN : nullptr, protos ? protos + b0 * way * ND : nullptr, st)))

@@ -37,6 +37,7 @@ struct arx_handle {
   // discriminator (model.py:183-204)
   float *dr_w = nullptr, *dr_b = nullptr, *d1_w = nullptr, *d1_b = nullptr;
   float *d2_w = nullptr, *d2_b = nullptr, *d3_w = nullptr, *d3_b = nullptr;
+  __half *wdr_img = nullptr;   // dimensionality_reduction weight as a tcgen05 B operand
   // support set
   int way = 0;
   int way_cap = 0;
@@ -104,6 +105,11 @@ int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t
 int arx_tc_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, cudaStream_t st);
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
                      int way, float *partial, float *logits, int32_t *chosen, int variant, cudaStream_t st);
+
+bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr);
+int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st);
+int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
+                         int way, const int32_t *chosen, float *y, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

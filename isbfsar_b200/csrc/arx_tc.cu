@@ -443,6 +443,285 @@ __global__ void k_finish_tc(const float *__restrict__ partial, float *__restrict
   if (chosen) chosen[b] = bi;
 }
 
+
+// =====================================================================================================
+// Open-set head pass (model.py:323-324,196): attention for the WINNING class of every window only, then
+//   y[q,l] = diff[q,:] . Wdr[l,:] + bdr[l]   as a third MMA:  Y[q,l]  M=128 (q on TMEM lanes), N=L, K=128 (d)
+// with A = diff^T written by the epilogue warps in the same MN-major layout as P (thread == d == K index)
+// and B = Wdr (L x 128, K-major).  One tile per window; operands: Kq[b], Kc[chosen[b]], Vc^T[chosen[b]].
+constexpr uint32_t H_OFF_KQ = 0;                       // 2 x 32 KB
+constexpr uint32_t H_OFF_KC = 2 * IMG_BYTES;           // 2 x 32 KB
+constexpr uint32_t H_OFF_VCT = 4 * IMG_BYTES;          // 32 KB
+constexpr uint32_t H_OFF_P = 5 * IMG_BYTES;            // P, then diff^T (shared), 32 KB
+constexpr uint32_t H_OFF_WDR = 6 * IMG_BYTES;          // up to 8 KB
+constexpr uint32_t H_OFF_BAR = 6 * IMG_BYTES + 8192;
+enum { HB_FULL_A = 0, HB_EMPTY_A = 2, HB_FULL_V = 4, HB_EMPTY_V = 5, HB_S_FULL = 6, HB_S_EMPTY = 8, HB_P_FULL = 10, HB_P_EMPTY = 11,
+       HB_O_FULL = 12, HB_O_EMPTY = 13, HB_DF_FULL = 14, HB_Y_FULL = 15, HB_Y_EMPTY = 16, HB_WDR = 17, HB_COUNT = 18 };
+constexpr uint32_t H_SMEM_BYTES = H_OFF_BAR + HB_COUNT * 8 + 16 + 1024;
+
+struct HeadParams {
+  const __half *kq_img, *kc_img, *vct_img, *wdr_img;
+  const float *G, *Vq, *dr_b;
+  const int32_t *chosen;
+  float *y;                // [n_win][N*L] fp32
+  int n_win, way, N, T, ldg, voff, L;
+};
+
+template <int Q2> __device__ __forceinline__ void diff_pair16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64]) {
+  constexpr int Q = 2 * Q2;
+  float d0 = 0.f, d1 = 0.f;
+  if constexpr (Q < 120) { constexpr int I = pair_i(Q, 16), J = pair_j(Q, 16); d0 = (a[I] + b[J]) - __uint_as_float(r[Q & 31]); }
+  if constexpr (Q + 1 < 120) { constexpr int I = pair_i(Q + 1, 16), J = pair_j(Q + 1, 16); d1 = (a[I] + b[J]) - __uint_as_float(r[(Q + 1) & 31]); }
+  pk[Q2] = pack_half2(d0, d1);
+}
+template <int CH, int... Js>
+__device__ __forceinline__ void diff_chunk16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64],
+                                             std::integer_sequence<int, Js...>) {
+  (diff_pair16<CH * 16 + Js>(a, b, r, pk), ...);
+}
+
+template <int MODE, int L>
+__global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + H_OFF_BAR);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + H_OFF_BAR + HB_COUNT * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = p.n_win > (int)blockIdx.x ? (p.n_win - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[HB_FULL_A + i], 1); mbar_init(&bars[HB_EMPTY_A + i], 1);
+      mbar_init(&bars[HB_S_FULL + i], 1); mbar_init(&bars[HB_S_EMPTY + i], 128);
+    }
+    mbar_init(&bars[HB_FULL_V], 1); mbar_init(&bars[HB_EMPTY_V], 1);
+    mbar_init(&bars[HB_P_FULL], 128); mbar_init(&bars[HB_P_EMPTY], 1);
+    mbar_init(&bars[HB_O_FULL], 1); mbar_init(&bars[HB_O_EMPTY], 128);
+    mbar_init(&bars[HB_DF_FULL], 128); mbar_init(&bars[HB_Y_FULL], 1); mbar_init(&bars[HB_Y_EMPTY], 128);
+    mbar_init(&bars[HB_WDR], 1);
+    mbar_init_fence();
+  }
+  if (warp == 3) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t TM_S = tmem, TM_O = tmem + 256, TM_Y = tmem + 384;
+  constexpr uint32_t WDR_BYTES = L * DD * 2;
+
+  if (warp == 0) {
+    if (elect_one()) {                 // producer A: Wdr once, then {Kq[b], Kc[chosen[b]]} per tile
+      mbar_arrive_expect_tx(&bars[HB_WDR], WDR_BYTES);
+      bulk_g2s(smem + H_OFF_WDR, p.wdr_img, WDR_BYTES, &bars[HB_WDR]);
+      for (int t = 0; t < ntiles; ++t) {
+        const int b = blockIdx.x + t * gridDim.x, c = p.chosen[b], sa = t & 1;
+        mbar_wait(&bars[HB_EMPTY_A + sa], ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[HB_FULL_A + sa], 2 * IMG_BYTES);
+        const uint8_t *kq = reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)b * IMG_BYTES;
+        const uint8_t *kc = reinterpret_cast<const uint8_t *>(p.kc_img) + (size_t)c * IMG_BYTES;
+        bulk_g2s(smem + H_OFF_KQ + sa * IMG_BYTES, kq, SUB_BYTES, &bars[HB_FULL_A + sa]);
+        bulk_g2s(smem + H_OFF_KQ + sa * IMG_BYTES + SUB_BYTES, kq + SUB_BYTES, SUB_BYTES, &bars[HB_FULL_A + sa]);
+        bulk_g2s(smem + H_OFF_KC + sa * IMG_BYTES, kc, SUB_BYTES, &bars[HB_FULL_A + sa]);
+        bulk_g2s(smem + H_OFF_KC + sa * IMG_BYTES + SUB_BYTES, kc + SUB_BYTES, SUB_BYTES, &bars[HB_FULL_A + sa]);
+      }
+    }
+  } else if (warp == 2) {
+    if (elect_one()) {                 // producer V: Vc^T[chosen[b]] per tile (single stage)
+      for (int t = 0; t < ntiles; ++t) {
+        const int b = blockIdx.x + t * gridDim.x, c = p.chosen[b];
+        mbar_wait(&bars[HB_EMPTY_V], (t & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars[HB_FULL_V], IMG_BYTES);
+        const uint8_t *vc = reinterpret_cast<const uint8_t *>(p.vct_img) + (size_t)c * IMG_BYTES;
+        bulk_g2s(smem + H_OFF_VCT, vc, SUB_BYTES, &bars[HB_FULL_V]);
+        bulk_g2s(smem + H_OFF_VCT + SUB_BYTES, vc + SUB_BYTES, SUB_BYTES, &bars[HB_FULL_V]);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint64_t DESC_K = smem_desc_sw128(16, 1024);
+      constexpr uint64_t DESC_MN = smem_desc_sw128(16384, 1024);
+      constexpr uint32_t IDESC1 = idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t IDESC2 = idesc_f16(128, 128, 0, 1);
+      constexpr uint32_t IDESC3 = idesc_f16(128, L, 1, 0);
+      const uint32_t sbase = smem_u32(smem);
+      mbar_wait(&bars[HB_WDR], 0);
+      auto mma1 = [&](int t) {
+        const int sa = t & 1;
+        mbar_wait(&bars[HB_FULL_A + sa], (t >> 1) & 1);
+        mbar_wait(&bars[HB_S_EMPTY + sa], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = sbase + H_OFF_KC + sa * IMG_BYTES, b0 = sbase + H_OFF_KQ + sa * IMG_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
+          mma_f16_ss(TM_S + sa * 128, smem_desc_at(DESC_K, a0 + off), smem_desc_at(DESC_K, b0 + off), IDESC1, kk > 0);
+        }
+        mma_commit(&bars[HB_S_FULL + sa]);
+        mma_commit(&bars[HB_EMPTY_A + sa]);
+      };
+      if (ntiles > 0) mma1(0);
+      for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) mma1(t + 1);
+        // MMA2: proto^T = Vc^T . P
+        mbar_wait(&bars[HB_P_FULL], t & 1);
+        mbar_wait(&bars[HB_FULL_V], t & 1);
+        mbar_wait(&bars[HB_O_EMPTY], (t & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
+          mma_f16_ss(TM_O, smem_desc_at(DESC_K, sbase + H_OFF_VCT + off), smem_desc_at(DESC_MN, sbase + H_OFF_P + kk * 2048), IDESC2, kk > 0);
+        }
+        mma_commit(&bars[HB_O_FULL]);
+        mma_commit(&bars[HB_EMPTY_V]);
+        // MMA3: Y = diff . Wdr^T   (A = diff^T image in the P buffer, MN-major; B = Wdr, K-major)
+        mbar_wait(&bars[HB_DF_FULL], t & 1);
+        mbar_wait(&bars[HB_Y_EMPTY], (t & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t boff = (kk >> 2) * (L * 128) + (kk & 3) * 32;
+          mma_f16_ss(TM_Y, smem_desc_at(DESC_MN, sbase + H_OFF_P + kk * 2048), smem_desc_at(DESC_K, sbase + H_OFF_WDR + boff), IDESC3, kk > 0);
+        }
+        mma_commit(&bars[HB_Y_FULL]);
+        mma_commit(&bars[HB_P_EMPTY]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int quad = warp - 4;
+    const int s = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t *row = smem + H_OFF_P + (s >> 3) * 1024 + (s & 7) * 128;
+    for (int t = 0; t < ntiles; ++t) {
+      const int sa = t & 1;
+      mbar_wait(&bars[HB_S_FULL + sa], (t >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[4][32];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld32(TM_S + lane_base + sa * 128 + ch * 32, r[ch]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[HB_S_EMPTY + sa]);
+      float z = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = fast_exp2(__uint_as_float(r[ch][j]));
+          r[ch][j] = __float_as_uint(e);
+          z += (ch * 32 + j < p.N) ? e : 0.f;
+        }
+      }
+      const float zinv = 1.0f / z;
+      mbar_wait(&bars[HB_P_EMPTY], (t & 1) ^ 1);
+#pragma unroll
+      for (int c16 = 0; c16 < 16; ++c16) {
+        const int ch = c16 >> 2, j0 = (c16 & 3) * 8;
+        uint4 v;
+        v.x = pack_half2(__uint_as_float(r[ch][j0 + 0]) * zinv, __uint_as_float(r[ch][j0 + 1]) * zinv);
+        v.y = pack_half2(__uint_as_float(r[ch][j0 + 2]) * zinv, __uint_as_float(r[ch][j0 + 3]) * zinv);
+        v.z = pack_half2(__uint_as_float(r[ch][j0 + 4]) * zinv, __uint_as_float(r[ch][j0 + 5]) * zinv);
+        v.w = pack_half2(__uint_as_float(r[ch][j0 + 6]) * zinv, __uint_as_float(r[ch][j0 + 7]) * zinv);
+        *reinterpret_cast<uint4 *>(row + (c16 >> 3) * 16384 + (((c16 & 7) ^ (s & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars[HB_P_FULL]);
+    }
+  } else if (warp >= 8) {
+    const int quad = warp - 8;
+    const int d = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t *row = smem + H_OFF_P + (d >> 3) * 1024 + (d & 7) * 128;
+    float bias[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) bias[l] = __ldg(p.dr_b + l);
+    for (int t = 0; t < ntiles; ++t) {
+      const int b = blockIdx.x + t * gridDim.x;
+      uint32_t pk[64];
+      uint32_t r[32];
+      if constexpr (MODE == 0) {
+        float a[16], bb[16];
+        const float *g0 = p.G + (size_t)b * 16 * p.ldg + p.voff + d;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { a[i] = __ldg(g0 + (size_t)i * p.ldg); bb[i] = __ldg(g0 + (size_t)i * p.ldg + DD); }
+        mbar_wait(&bars[HB_O_FULL], t & 1);
+        tc_fence_after();
+        tmem_ld32(TM_O + lane_base + 0, r); tmem_ld_wait();
+        diff_chunk16<0>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        tmem_ld32(TM_O + lane_base + 32, r); tmem_ld_wait();
+        diff_chunk16<1>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        tmem_ld32(TM_O + lane_base + 64, r); tmem_ld_wait();
+        diff_chunk16<2>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        tmem_ld32(TM_O + lane_base + 96, r); tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[HB_O_EMPTY]);
+        diff_chunk16<3>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+      } else {
+        const float *vq = p.Vq + (size_t)b * p.N * DD + d;
+        mbar_wait(&bars[HB_O_FULL], t & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          tmem_ld32(TM_O + lane_base + ch * 32, r); tmem_ld_wait();
+          if (ch == 3) { tc_fence_before(); mbar_arrive(&bars[HB_O_EMPTY]); }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int q = ch * 32 + j;
+            const float d0 = q < p.N ? __ldg(vq + (size_t)q * DD) - __uint_as_float(r[j]) : 0.f;
+            const float d1 = q + 1 < p.N ? __ldg(vq + (size_t)(q + 1) * DD) - __uint_as_float(r[j + 1]) : 0.f;
+            pk[q >> 1] = pack_half2(d0, d1);
+          }
+        }
+      }
+      // diff^T[d, :] -> A operand of MMA3 (MN-major: memory row = d, 64 query tuples per 128-byte row); the P
+      // buffer is free: o_full implies MMA2 has finished reading it
+#pragma unroll
+      for (int c16 = 0; c16 < 16; ++c16) {
+        uint4 v = make_uint4(pk[c16 * 4 + 0], pk[c16 * 4 + 1], pk[c16 * 4 + 2], pk[c16 * 4 + 3]);
+        *reinterpret_cast<uint4 *>(row + (c16 >> 3) * 16384 + (((c16 & 7) ^ (d & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars[HB_DF_FULL]);
+      // Y[q, 0..L) for q = this thread's TMEM lane
+      mbar_wait(&bars[HB_Y_FULL], t & 1);
+      tc_fence_after();
+      uint32_t yv[L];
+      if constexpr (L == 16) {
+        tmem_ld16(TM_Y + lane_base, yv);
+      } else {
+        tmem_ld32(TM_Y + lane_base, yv);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bars[HB_Y_EMPTY]);
+      const int q = d;    // lane index doubles as the query tuple for the Y tile
+      if (q < p.N) {
+        float *dst = p.y + ((size_t)b * p.N + q) * L;
+#pragma unroll
+        for (int l = 0; l < L; l += 4)
+          *reinterpret_cast<float4 *>(dst + l) = make_float4(__uint_as_float(yv[l]) + bias[l], __uint_as_float(yv[l + 1]) + bias[l + 1],
+                                                             __uint_as_float(yv[l + 2]) + bias[l + 2], __uint_as_float(yv[l + 3]) + bias[l + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// Wdr image: B operand of MMA3, K-major SW128: [L rows x 64 d] sub-tiles (L*128 bytes each), from fp32 (L, 128)
+__global__ void k_prep_wdr_img(const float *__restrict__ w, __half *__restrict__ img, int L) {
+  uint8_t *out = reinterpret_cast<uint8_t *>(img);
+  for (int e = threadIdx.x; e < L * 16; e += blockDim.x) {
+    const int dc = e & 15, l = e >> 4;
+    const float4 x0 = *reinterpret_cast<const float4 *>(w + (size_t)l * DD + dc * 8);
+    const float4 x1 = *reinterpret_cast<const float4 *>(w + (size_t)l * DD + dc * 8 + 4);
+    uint4 pk;
+    pk.x = pack_half2(x0.x, x0.y); pk.y = pack_half2(x0.z, x0.w); pk.z = pack_half2(x1.x, x1.y); pk.w = pack_half2(x1.z, x1.w);
+    const int d0 = dc * 8;
+    *reinterpret_cast<uint4 *>(out + (d0 >> 6) * (L * 128) + sw128_offset(l, d0 & 63)) = pk;
+  }
+}
+
 }  // namespace
 
 bool arx_tc_supported(const arx_handle *h, const ArxTransformer &tr) {
@@ -484,6 +763,38 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
   kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   k_finish_tc<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
+}
+
+bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr) {
+  return arx_tc_supported(h, tr) && (h->T == 16 || h->T == 32) && h->cfg.has_discriminator;
+}
+
+int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st) {
+  if (!h->cfg.has_discriminator || (h->T != 16 && h->T != 32)) return ARX_OK;
+  if (!h->wdr_img) ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->wdr_img), (size_t)h->T * DD * 2));
+  k_prep_wdr_img<<<1, 256, 0, st>>>(h->dr_w, h->wdr_img, h->T);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
+}
+
+// y (n_win, N*T) fp32 = dimensionality_reduction(diff of the winning class), computed on tensor cores
+int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
+                         int way, const int32_t *chosen, float *y, cudaStream_t st) {
+  HeadParams p{};
+  p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.wdr_img = h->wdr_img; p.G = G; p.Vq = Vq; p.dr_b = h->dr_b;
+  p.chosen = chosen; p.y = y; p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = 2 * tr.c * h->D; p.voff = tr.c * h->D;
+  p.L = h->T;
+  const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
+  if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_head: generic epilogue needs Vq");
+  void (*kern)(const HeadParams) = nullptr;
+  if (h->T == 16) kern = mode0 ? k_head_tc<0, 16> : k_head_tc<1, 16>;
+  else if (h->T == 32) kern = k_head_tc<1, 32>;
+  else return arx_fail(h, ARX_ERR_INVALID, "tc_head: unsupported seq_len");
+  const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
+  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H_SMEM_BYTES));
+  kern<<<grid, NTHREADS, H_SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }
