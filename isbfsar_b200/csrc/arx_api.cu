@@ -86,32 +86,40 @@ void free_support(arx_handle *h) {
 // per-window workspace of the fp32 path
 struct Fp32Ws {
   float *H1, *FE, *G, *Kq, *Vq, *Z, *partial, *y, *h1, *h2;
-  __half *kq_img;
+  __half *kq_img, *x_img, *h_img, *f_img, *y_img, *h1_img;
   size_t bytes;
 };
 Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, void *base,
-                  bool tc = false, bool tuples32 = true) {
+                  bool tc = false, bool tuples32 = true, bool tcl = false, bool tc_head = false) {
   Carver c(base);
   Fp32Ws w{};
   const int nb = tc ? 4 : (tr.N + 63) / 64;
   w.kq_img = tc ? c.take<__half>(n * 128 * 128) : nullptr;
-  w.H1 = from_frames ? c.take<float>(n * h->T * h->H) : nullptr;
-  w.FE = from_frames ? c.take<float>(n * h->T * h->F) : nullptr;
+  const int64_t rows_pad = (n * h->T + 127) / 128 * 128, n_pad = (n + 127) / 128 * 128;
+  w.x_img = (tcl && from_frames) ? c.take<__half>(rows_pad * 128) : nullptr;
+  w.h_img = (tcl && from_frames) ? c.take<__half>(rows_pad * 192) : nullptr;
+  w.f_img = tcl ? c.take<__half>(rows_pad * 256) : nullptr;
+  w.y_img = (tcl && tc_head && disc) ? c.take<__half>(n_pad * (int64_t)h->tl_d1.nk * 64) : nullptr;
+  w.h1_img = (tcl && tc_head && disc) ? c.take<__half>(n_pad * 256) : nullptr;
+  w.H1 = (from_frames && !tcl) ? c.take<float>(n * h->T * h->H) : nullptr;
+  w.FE = (from_frames && !tcl) ? c.take<float>(n * h->T * h->F) : nullptr;
   w.G = c.take<float>(n * h->T * 2 * tr.c * h->D);
   w.Kq = tuples32 ? c.take<float>(n * tr.N * h->D) : nullptr;
   w.Vq = tuples32 ? c.take<float>(n * tr.N * h->D) : nullptr;
   w.Z = tuples32 ? c.take<float>(n * way * tr.N * 2) : nullptr;
   w.partial = c.take<float>(n * way * nb);
-  w.y = disc ? c.take<float>(n * tr.N * h->T) : nullptr;
-  w.h1 = disc ? c.take<float>(n * 256) : nullptr;
-  w.h2 = disc ? c.take<float>(n * 64) : nullptr;
+  const bool disc32 = disc && !(tcl && tc_head);
+  w.y = disc32 ? c.take<float>(n * tr.N * h->T) : nullptr;
+  w.h1 = disc32 ? c.take<float>(n * 256) : nullptr;
+  w.h2 = disc32 ? c.take<float>(n * 64) : nullptr;
   w.bytes = c.off + 256;
   return w;
 }
 
 int64_t pick_chunk(arx_handle *h, const ArxTransformer &tr, int way, bool from_frames, bool disc, int64_t n_total, bool tc,
-                   bool tuples32) {
-  Fp32Ws one = carve_fp32(h, tr, 1, way, from_frames, disc, nullptr, tc, tuples32);
+                   bool tuples32, bool tcl, bool tc_head) {
+  Fp32Ws one = carve_fp32(h, tr, 128, way, from_frames, disc, nullptr, tc, tuples32, tcl, tc_head);
+  one.bytes = one.bytes / 128 + 1;
   int64_t cap = h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096;
   const size_t budget = (size_t)3 << 30;
   int64_t fit = (int64_t)(budget / one.bytes);
@@ -214,6 +222,8 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
   cudaFree(h->wdr_img);
+  for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2}) { cudaFree(L->w_img); cudaFree(L->bias); }
+  for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) { cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); }
   cudaFree(h->ws);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
@@ -277,6 +287,22 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     if (h->cfg.force_path != 1 && (rc = arx_tc_prep_head_weights(h, st))) return rc;
   }
 #undef UP
+  // tensor-core images of the linear layers (fp16, pre-swizzled); shapes outside these bounds stay on the fp32 kernels
+  h->tc_linears = false;
+  if (h->cfg.force_path != 1 && h->F == 256 && h->H <= 192 && h->J3 <= 128) {
+    if ((rc = arx_tc_linear_prepare(h, h->tl_fc1, h->fc1_w, h->J3, h->fc1_b, h->H, h->J3, 192, st))) return rc;
+    if ((rc = arx_tc_linear_prepare(h, h->tl_fc2, h->fc2_w, h->H, h->fc2_b, h->F, h->H, 256, st))) return rc;
+    for (int i = 0; i < h->cfg.n_transformers; ++i) {
+      ArxTransformer &tr = h->tr[i];
+      if ((rc = arx_tc_linear_prepare(h, tr.tl_proj, tr.wp, h->F, nullptr, 2 * tr.c * h->D, h->F, 256, st))) return rc;
+    }
+    if (h->cfg.has_discriminator) {
+      const int K1 = h->T * (h->T - 1) / 2 * h->T;
+      if ((rc = arx_tc_linear_prepare(h, h->tl_d1, h->d1_w, K1, h->d1_b, 256, K1, 256, st))) return rc;
+      if ((rc = arx_tc_linear_prepare(h, h->tl_d2, h->d2_w, 256, h->d2_b, 64, 256, 64, st))) return rc;
+    }
+    h->tc_linears = true;
+  }
   ARX_CUDA(h, cudaStreamSynchronize(st));
   h->weights_loaded = true;
   free_support(h);   // support operands depend on the weights
@@ -456,26 +482,42 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const bool mode0 = use_tc && h->T == 16 && tr.c == 2;
   const bool tc_head = use_tc && disc && arx_tc_head_supported(h, tr) && (h->tc_variant & 2) == 0;
   const bool tuples32 = !use_tc || (disc && !tc_head) || !mode0;    // fp32 tuple tensors: fp32 path/head pass, generic epilogue
-  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32);
-  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32);
+  const bool tcl = use_tc && h->tc_linears && (h->tc_variant & 4) == 0;
+  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32, tcl, tc_head);
+  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32, tcl, tc_head);
   size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
   int rc = arx_ws_reserve(h, sz.bytes + extra);
   if (rc) return rc;
-  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, use_tc, tuples32);
+  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, use_tc, tuples32, tcl, tc_head);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
   h->last_path = use_tc ? 2 : 1;
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
     const int64_t n = std::min(chunk, n_windows - b0);
     const float *FE;
     if ((rc = prof_mark(h, 0, st))) return rc;
-    if (from_frames) {
-      if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, n * h->T, w.H1, w.FE, st))) return rc;
-      FE = w.FE;
+    const int64_t rows = n * h->T;
+    if (tcl) {
+      // frame MLP + projection on tensor cores, activations chained as fp16 images
+      FE = nullptr;
+      if (from_frames) {
+        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, tr.tl_proj.nk, st))) return rc;
+      } else {
+        if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, tr.tl_proj.nk, st))) return rc;
+      }
+      if ((rc = prof_mark(h, 1, st))) return rc;
+      if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, rows, w.G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
     } else {
-      FE = qfeats_dev + b0 * h->T * h->F;
+      if (from_frames) {
+        if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, rows, w.H1, w.FE, st))) return rc;
+        FE = w.FE;
+      } else {
+        FE = qfeats_dev + b0 * h->T * h->F;
+      }
+      if ((rc = prof_mark(h, 1, st))) return rc;
+      if ((rc = project_frames(h, tr, FE, rows, w.G, st))) return rc;
     }
-    if ((rc = prof_mark(h, 1, st))) return rc;
-    if ((rc = project_frames(h, tr, FE, n * h->T, w.G, st))) return rc;
     if ((rc = prof_mark(h, 2, st))) return rc;
     if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
     if (use_tc && (rc = arx_tc_prep_query(h, tr, w.G, n, w.kq_img, st))) return rc;
@@ -487,7 +529,9 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
                                  h->tc_variant, st)))
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
-      if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, st))) return rc;
+      if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
+                                                        h->tl_d1.nk, st)))
+        return rc;
       if (disc && !tc_head && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
     } else {
       if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
@@ -495,7 +539,10 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
     }
-    if (disc) {
+    if (disc && w.y_img) {
+      if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, st))) return rc;
+      if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true_dev + b0, st))) return rc;
+    } else if (disc) {
       const int K1 = tr.N * h->T;
       if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
       if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;

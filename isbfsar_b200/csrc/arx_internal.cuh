@@ -9,6 +9,13 @@
 
 #define ARX_SOFTMAX_LOG2E 1.4426950408889634f
 
+// A linear layer prepared for the tcgen05 GEMM: fp16 weight image [n_tiles][nk][BN x 64] + zero-padded bias
+struct ArxTcLinear {
+  __half *w_img = nullptr;
+  float *bias = nullptr;
+  int N = 0, K = 0, BN = 0, n_tiles = 0, nk = 0;
+};
+
 struct ArxTransformer {
   int c = 0;            // tuple cardinality
   int N = 0;            // C(T,c)
@@ -23,6 +30,7 @@ struct ArxTransformer {
   // support operands, tcgen05 path: fp16 UMMA smem images, see arx_tc.cu
   __half *ks_img = nullptr, *vs_img = nullptr;
   float softmax_bound = 0.f; // static |S| bound from LayerNorm affine
+  ArxTcLinear tl_proj;       // K/V projection (2cD x F) on tensor cores
 };
 
 struct arx_handle {
@@ -38,6 +46,8 @@ struct arx_handle {
   float *dr_w = nullptr, *dr_b = nullptr, *d1_w = nullptr, *d1_b = nullptr;
   float *d2_w = nullptr, *d2_b = nullptr, *d3_w = nullptr, *d3_b = nullptr;
   __half *wdr_img = nullptr;   // dimensionality_reduction weight as a tcgen05 B operand
+  ArxTcLinear tl_fc1, tl_fc2, tl_d1, tl_d2;
+  bool tc_linears = false;     // frame MLP / projection / discriminator MLP run on tensor cores
   // support set
   int way = 0;
   int way_cap = 0;
@@ -109,7 +119,16 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
 bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st);
 int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                         int way, const int32_t *chosen, float *y, cudaStream_t st);
+                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, cudaStream_t st);
+
+// ---- tcgen05 GEMM (arx_gemm_tc.cu) ------------------------------------------------
+int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw, const float *bias, int N, int K, int BN, cudaStream_t st);
+int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, cudaStream_t st);
+int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, cudaStream_t st);
+int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
+                      cudaStream_t st);
+int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, const float *w3, const float *b3, float *out,
+                              cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

@@ -463,8 +463,9 @@ struct HeadParams {
   const __half *kq_img, *kc_img, *vct_img, *wdr_img;
   const float *G, *Vq, *dr_b;
   const int32_t *chosen;
-  float *y;                // [n_win][N*L] fp32
-  int n_win, way, N, T, ldg, voff, L;
+  float *y;                // [n_win][N*L] fp32, or
+  __half *y_img;           // fp16 activation image [ceil(n_win/128)][y_nk][128 x 64] for the tcgen05 GEMM of fc1
+  int n_win, way, N, T, ldg, voff, L, y_nk;
 };
 
 template <int Q2> __device__ __forceinline__ void diff_pair16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64]) {
@@ -694,7 +695,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
       tc_fence_before();
       mbar_arrive(&bars[HB_Y_EMPTY]);
       const int q = d;    // lane index doubles as the query tuple for the Y tile
-      if (q < p.N) {
+      if (q < p.N && p.y_img) {
+        const int col = q * L;
+        uint8_t *dst = reinterpret_cast<uint8_t *>(p.y_img) + ((size_t)(b >> 7) * p.y_nk + (col >> 6)) * (128 * 128);
+#pragma unroll
+        for (int l = 0; l < L; l += 8) {
+          uint4 pk;
+          pk.x = pack_half2(__uint_as_float(yv[l + 0]) + bias[l + 0], __uint_as_float(yv[l + 1]) + bias[l + 1]);
+          pk.y = pack_half2(__uint_as_float(yv[l + 2]) + bias[l + 2], __uint_as_float(yv[l + 3]) + bias[l + 3]);
+          pk.z = pack_half2(__uint_as_float(yv[l + 4]) + bias[l + 4], __uint_as_float(yv[l + 5]) + bias[l + 5]);
+          pk.w = pack_half2(__uint_as_float(yv[l + 6]) + bias[l + 6], __uint_as_float(yv[l + 7]) + bias[l + 7]);
+          *reinterpret_cast<uint4 *>(dst + sw128_offset(b & 127, (col & 63) + l)) = pk;
+        }
+      } else if (q < p.N) {
         float *dst = p.y + ((size_t)b * p.N + q) * L;
 #pragma unroll
         for (int l = 0; l < L; l += 4)
@@ -781,8 +794,9 @@ int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st) {
 
 // y (n_win, N*T) fp32 = dimensionality_reduction(diff of the winning class), computed on tensor cores
 int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                         int way, const int32_t *chosen, float *y, cudaStream_t st) {
+                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, cudaStream_t st) {
   HeadParams p{};
+  p.y_img = y_img; p.y_nk = y_nk;
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.wdr_img = h->wdr_img; p.G = G; p.Vq = Vq; p.dr_b = h->dr_b;
   p.chosen = chosen; p.y = y; p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = 2 * tr.c * h->D; p.voff = tr.c * h->D;
   p.L = h->T;
