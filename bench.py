@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=WINDOWS_PER_GPU, help="query windows per GPU per step")
     ap.add_argument("--force-path", type=int, default=0, help="0 auto, 1 fp32 kernels, 2 tcgen05 kernels")
+    ap.add_argument("--chunk", type=int, default=0, help="windows per internal pass of arx_score (0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -183,7 +184,7 @@ def main():
 
     cfg = Cfg()
     B = args.windows
-    model, sd = make_model(cfg, 0, force_path=args.force_path)
+    model, sd = make_model(cfg, 0, force_path=args.force_path, max_chunk=args.chunk)
     support, labels, query, planted = make_episode(cfg, B, 1 + rank, "structured")
     # every rank scores ITS OWN B windows (weak scaling); the support set is rank 0's
     support0 = make_episode(cfg, 1, 1, "structured")[0]

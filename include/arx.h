@@ -158,6 +158,9 @@ ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t
 /* Debug knobs for kernel bring-up and tests.  key 0: tcgen05 attention variant (bit 0 = K-major
  * layout of the P operand instead of MN-major). */
 ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
+/* key 1 (value != 0) arms a timeline trace of CTA 0 of the attention kernel; this reads it back:
+ * host_out[3 roles][64 tiles][8 stamps] of SM clock values (bring-up tool). */
+ARX_API int arx_debug_read_trace(arx_handle *h, long long *host_out);
 
 /* Introspection for tests/bench: kernel launches issued by this handle so far,
  * and which attention path the last arx_score used (1 = fp32, 2 = tcgen05). */

@@ -15,7 +15,7 @@ EXPORTS = [
     "arx_tuple_table", "arx_embed", "arx_set_support_poses", "arx_set_support_features",
     "arx_get_support_features", "arx_support_way", "arx_support_blob_bytes", "arx_export_support",
     "arx_import_support", "arx_score", "arx_score_features", "arx_debug_attention", "arx_score_host",
-    "arx_decode_heatmaps", "arx_launch_count", "arx_last_path", "arx_profile_enable", "arx_profile_read", "arx_debug_set",
+    "arx_decode_heatmaps", "arx_launch_count", "arx_last_path", "arx_profile_enable", "arx_profile_read", "arx_debug_set", "arx_debug_read_trace",
 ]
 
 
@@ -81,6 +81,7 @@ def load() -> C.CDLL:
         "arx_launch_count": (I64, [H]),
         "arx_last_path": (C.c_int, [H]),
         "arx_debug_set": (C.c_int, [H, I32, I32]),
+        "arx_debug_read_trace": (C.c_int, [H, C.POINTER(C.c_longlong)]),
         "arx_profile_enable": (C.c_int, [H, I32]),
         "arx_profile_read": (C.c_int, [H, C.POINTER(C.c_double), C.POINTER(I64), I32]),
     }

@@ -74,9 +74,9 @@ int upload(arx_handle *h, float *dst, const float *src, size_t n, bool on_device
 void free_support(arx_handle *h) {
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
     cudaFree(h->tr[i].ks); cudaFree(h->tr[i].vs);
-    cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img);
+    cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img); cudaFree(h->tr[i].vs_img_bf);
     h->tr[i].ks = h->tr[i].vs = nullptr;
-    h->tr[i].ks_img = h->tr[i].vs_img = nullptr;
+    h->tr[i].ks_img = h->tr[i].vs_img = h->tr[i].vs_img_bf = nullptr;
   }
   cudaFree(h->ss_feat);
   h->ss_feat = nullptr;
@@ -217,7 +217,7 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->fc1_w); cudaFree(h->fc1_b); cudaFree(h->fc2_w); cudaFree(h->fc2_b);
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     ArxTransformer &tr = h->tr[i];
-    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples);
+    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots);
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
@@ -225,6 +225,7 @@ void arx_destroy(arx_handle *h) {
   for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2}) { cudaFree(L->w_img); cudaFree(L->bias); }
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) { cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); }
   cudaFree(h->ws);
+  cudaFree(h->ss_scratch);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     cudaFree(h->dev_in[i]); cudaFree(h->dev_out[i]);
@@ -371,12 +372,18 @@ int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, vo
   if (!h || !poses_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
   if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float *feats = nullptr;
-  ARX_CUDA(h, cudaMalloc(&feats, (size_t)way * h->T * h->F * sizeof(float)));
-  int rc = arx_embed(h, poses_dev, (int64_t)way * h->T, feats, st);
-  if (rc == ARX_OK) rc = arx_set_support_features(h, feats, way, st);
-  cudaStreamSynchronize(st);
-  cudaFree(feats);
+  // features go through a handle-owned scratch buffer (grown rarely), then the common path
+  const size_t need = (size_t)way * h->T * h->F * sizeof(float);
+  if (need > h->ss_scratch_bytes) {
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    cudaFree(h->ss_scratch);
+    h->ss_scratch = nullptr;
+    h->ss_scratch_bytes = 0;
+    ARX_CUDA(h, cudaMalloc(&h->ss_scratch, need));
+    h->ss_scratch_bytes = need;
+  }
+  int rc = arx_embed(h, poses_dev, (int64_t)way * h->T, static_cast<float *>(h->ss_scratch), st);
+  if (rc == ARX_OK) rc = arx_set_support_features(h, static_cast<float *>(h->ss_scratch), way, st);
   return rc;
 }
 
@@ -520,7 +527,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     }
     if ((rc = prof_mark(h, 2, st))) return rc;
     if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
-    if (use_tc && (rc = arx_tc_prep_query(h, tr, w.G, n, w.kq_img, st))) return rc;
+    if (use_tc && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
@@ -589,7 +596,8 @@ int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, fl
   const int way = h->way;
   const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);
   const size_t out_per = (size_t)(way + 2) * sizeof(float);   // logits | is_true | chosen
-  const int64_t stage = std::min<int64_t>(n_windows, h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096);
+  // copy/compute overlap needs several chunks per call: stage at most 1024 windows at a time
+  const int64_t stage = std::min<int64_t>(n_windows, std::min<int64_t>(h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096, 1024));
   if ((size_t)stage > h->stage_windows || way != h->stage_way) {
     // (re)allocate staging sized for `stage` windows at the current way
     ARX_CUDA(h, cudaDeviceSynchronize());
@@ -668,7 +676,23 @@ int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset) 
 int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
   if (!h) return ARX_ERR_INVALID;
   if (key == 0) { h->tc_variant = value; return ARX_OK; }
+  if (key == 1) {   // allocate (value != 0) / free the kernel timeline trace buffer: 3 roles x 64 tiles x 8 stamps
+    if (value && !h->trace_buf) {
+      ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->trace_buf), 3 * 64 * 8 * sizeof(long long)));
+      ARX_CUDA(h, cudaMemset(h->trace_buf, 0, 3 * 64 * 8 * sizeof(long long)));
+    } else if (!value && h->trace_buf) {
+      cudaFree(h->trace_buf);
+      h->trace_buf = nullptr;
+    }
+    return ARX_OK;
+  }
   return arx_fail(h, ARX_ERR_INVALID, "debug_set: unknown key %d", key);
+}
+
+int arx_debug_read_trace(arx_handle *h, long long *host_out) {
+  if (!h || !host_out || !h->trace_buf) return ARX_ERR_INVALID;
+  ARX_CUDA(h, cudaMemcpy(host_out, h->trace_buf, 3 * 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return ARX_OK;
 }
 
 int64_t arx_launch_count(const arx_handle *h) { return h ? h->launches : 0; }

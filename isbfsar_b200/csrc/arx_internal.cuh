@@ -25,10 +25,12 @@ struct ArxTransformer {
   float *bp = nullptr;      // (2cD): k bias on K part 0, v bias on V part 0, zero elsewhere
   float *ln_g = nullptr, *ln_b = nullptr;
   int32_t *tuples = nullptr; // (N,c) int32, built on device
+  int32_t *q_slots = nullptr; // (128,2) internal padded-triangular order of the query tuples (T=16 pairs), -1 = pad
   // support operands, fp32 generic path: (W,N,D) each
   float *ks = nullptr, *vs = nullptr;
   // support operands, tcgen05 path: fp16 UMMA smem images, see arx_tc.cu
   __half *ks_img = nullptr, *vs_img = nullptr;
+  __half *vs_img_bf = nullptr;   // Vc^T as bf16 (prototype MMA of arx_tc2.cu)
   float softmax_bound = 0.f; // static |S| bound from LayerNorm affine
   ArxTcLinear tl_proj;       // K/V projection (2cD x F) on tensor cores
 };
@@ -52,6 +54,8 @@ struct arx_handle {
   int way = 0;
   int way_cap = 0;
   float *ss_feat = nullptr;   // (W,T,F)
+  void *ss_scratch = nullptr;
+  size_t ss_scratch_bytes = 0;
   // workspace (grown on demand)
   void *ws = nullptr;
   size_t ws_bytes = 0;
@@ -72,6 +76,7 @@ struct arx_handle {
   double prof_ms[ARX_N_STAGES] = {0, 0, 0, 0, 0};
   int64_t prof_chunks = 0;
   int last_path = 0;
+  long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int tc_variant = 0;   // debug: bit 0 selects the K-major P layout
   std::string err;
 };
@@ -112,7 +117,8 @@ int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float 
 // ---- tcgen05 kernels (arx_tc.cu) -------------------------------------------------
 bool arx_tc_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
-int arx_tc_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, cudaStream_t st);
+int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st);
+bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
                      int way, float *partial, float *logits, int32_t *chosen, int variant, cudaStream_t st);
 
@@ -129,6 +135,29 @@ int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, 
                       cudaStream_t st);
 int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, const float *w3, const float *b3, float *out,
                               cudaStream_t st);
+
+// ---- padded-triangular slot order of the C(16,2) pairs (shared with the host-side slot table) ---------
+// row i: i even -> slots for j = i..15 (the j == i slot is a pad), i odd -> j = i+1..15; every row has even length.
+__host__ __device__ constexpr int arx_slot_row_len(int i) { return (i % 2 == 0) ? 16 - i : 15 - i; }
+__host__ __device__ constexpr int arx_slot_row_start(int i) {
+  int s = 0;
+  for (int k = 0; k < i; ++k) s += arx_slot_row_len(k);
+  return s;
+}
+__host__ __device__ constexpr int arx_slot_i(int q) {
+  int i = 0;
+  while (q >= arx_slot_row_start(i + 1)) ++i;
+  return i;
+}
+__host__ __device__ constexpr int arx_slot_j(int q) {   // == i for a pad slot
+  const int i = arx_slot_i(q), off = q - arx_slot_row_start(i);
+  return (i % 2 == 0) ? i + off : i + 1 + off;
+}
+static_assert(arx_slot_row_start(16) == 128, "slot layout must fill the 128-column tile exactly");
+
+void arx_tc2_slot_table(int32_t *out /* 256 */);
+int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
+                             float *partial, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

@@ -16,6 +16,7 @@
 // Class operands are reused by GROUP=2 windows per load; everything is double-buffered through mbarriers.
 #include "arx_internal.cuh"
 #include "arx_ptx.cuh"
+#include <cuda_bf16.h>
 #include <utility>
 
 namespace {
@@ -46,7 +47,11 @@ struct AttnParams {
   const float *Vq;         // [n_win][N][D] fp32 tuple values                                     (MODE 1)
   float *partial;          // [n_win][way][4]
   int n_win, way, N, T, ldg, voff;
+  long long *trace;        // optional per-role timestamps of CTA 0 (bring-up tool), [role][tile][8]
 };
+
+#define ARX_TRACE_TILES 64
+#define TRACE(role, tile, k) do { if (p.trace && blockIdx.x == 0 && (tile) < ARX_TRACE_TILES) p.trace[(((role) * ARX_TRACE_TILES) + (tile)) * 8 + (k)] = clock64(); } while (0)
 
 struct TileIter {
   int n_win, way, n_groups, gstride;
@@ -100,6 +105,12 @@ __device__ __forceinline__ void acc_chunk16(const float (&a)[16], const float (&
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// volatile: keeps the MUFU ops of a row in one back-to-back batch
+__device__ __forceinline__ uint32_t ex2_bits(uint32_t x) {
+  uint32_t y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
@@ -187,6 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tc(const AttnParams p) {
         if (it1.w == 0) mbar_wait(&bars[B_FULL_C + st], (cc >> 1) & 1);
         mbar_wait(&bars[B_S_EMPTY + buf], ((f1 >> 1) & 1) ^ 1);
         tc_fence_after();
+        TRACE(0, f1, 0);
         const uint32_t a0 = sbase + OFF_KC + st * IMG_BYTES, b0 = sbase + OFF_KQ + it1.w * IMG_BYTES;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -199,9 +211,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tc(const AttnParams p) {
       };
       auto mma2 = [&]() {
         const int cc = it2.cls_counter(), st = cc & 1, buf = f2 & 1;
+        TRACE(0, f2, 1);
         mbar_wait(&bars[B_P_FULL], f2 & 1);
+        TRACE(0, f2, 2);
         mbar_wait(&bars[B_O_EMPTY + buf], ((f2 >> 1) & 1) ^ 1);
         tc_fence_after();
+        TRACE(0, f2, 3);
         const uint32_t a0 = sbase + OFF_VCT + st * IMG_BYTES, b0 = sbase + OFF_P;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -230,35 +245,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tc(const AttnParams p) {
     int f = 0;
     while (it.valid) {
       const int buf = f & 1;
+      if (threadIdx.x == 128) TRACE(1, f, 0);
       mbar_wait(&bars[B_S_FULL + buf], (f >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 128) TRACE(1, f, 1);
       uint32_t r[4][32];
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) tmem_ld32(TM_S + lane_base + buf * 128 + ch * 32, r[ch]);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bars[B_S_EMPTY + buf]);
-      float z = 0.f;
+      if (threadIdx.x == 128) TRACE(1, f, 2);
+      // exp2 of the whole row first (128 independent MUFU ops, 8 clk each: the MUFU floor), the sums afterwards on
+      // four independent accumulators -- keeps the in-order issue from stalling on the MUFU->FADD latency
+      float zp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[ch][j] = ex2_bits(r[ch][j]);
+      }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         if ((ch + 1) * 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = fast_exp2(__uint_as_float(r[ch][j]));
-            r[ch][j] = __float_as_uint(e);
-            z += e;
-          }
+          for (int j = 0; j < 32; ++j) zp[j & 3] += __uint_as_float(r[ch][j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = fast_exp2(__uint_as_float(r[ch][j]));
-            r[ch][j] = __float_as_uint(e);
-            z += (ch * 32 + j < p.N) ? e : 0.f;
-          }
+          for (int j = 0; j < 32; ++j) zp[j & 3] += (ch * 32 + j < p.N) ? __uint_as_float(r[ch][j]) : 0.f;
         }
       }
-      const float zinv = 1.0f / z;
+      const float z = (zp[0] + zp[1]) + (zp[2] + zp[3]);
+      const float zinv = __frcp_rn(z);
+      if (threadIdx.x == 128) TRACE(1, f, 3);
       mbar_wait(&bars[B_P_EMPTY], (f & 1) ^ 1);
+      if (threadIdx.x == 128) TRACE(1, f, 4);
       if constexpr (P_MN) {
         // B operand, MN-major SW128: memory row = support tuple s (K index), 64 query tuples per 128-byte row
         uint8_t *row = pbuf + (s >> 3) * 1024 + (s & 7) * 128;
@@ -282,8 +302,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tc(const AttnParams p) {
           *reinterpret_cast<__half *>(col + q * 128 + ((sc ^ (q & 7)) << 4)) = hv;
         }
       }
+      if (threadIdx.x == 128) TRACE(1, f, 5);
       fence_proxy_async_smem();
       mbar_arrive(&bars[B_P_FULL]);
+      if (threadIdx.x == 128) TRACE(1, f, 6);
       ++f; it.next();
     }
   } else if (warp >= 8) {
@@ -309,22 +331,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tc(const AttnParams p) {
         }
       }
       const int buf = f & 1;
+      if (threadIdx.x == 256) TRACE(2, f, 0);
       mbar_wait(&bars[B_O_FULL + buf], (f >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 256) TRACE(2, f, 1);
       float acc = 0.f;
       uint32_t r[32];
       if constexpr (MODE == 0) {
         auto run = [&](const float (&a)[16], const float (&b)[16]) {
-          tmem_ld32(TM_O + lane_base + buf * 128 + 0, r); tmem_ld_wait();
+          uint32_t r2[32];
+          tmem_ld32(TM_O + lane_base + buf * 128 + 0, r);
+          tmem_ld32(TM_O + lane_base + buf * 128 + 32, r2);
+          tmem_ld_wait();
           acc_chunk16<0>(a, b, r, acc, std::make_integer_sequence<int, 32>{});
-          tmem_ld32(TM_O + lane_base + buf * 128 + 32, r); tmem_ld_wait();
-          acc_chunk16<1>(a, b, r, acc, std::make_integer_sequence<int, 32>{});
-          tmem_ld32(TM_O + lane_base + buf * 128 + 64, r); tmem_ld_wait();
+          tmem_ld32(TM_O + lane_base + buf * 128 + 64, r);
+          acc_chunk16<1>(a, b, r2, acc, std::make_integer_sequence<int, 32>{});
+          tmem_ld_wait();
+          tmem_ld32(TM_O + lane_base + buf * 128 + 96, r2);
           acc_chunk16<2>(a, b, r, acc, std::make_integer_sequence<int, 32>{});
-          tmem_ld32(TM_O + lane_base + buf * 128 + 96, r); tmem_ld_wait();
+          tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&bars[B_O_EMPTY + buf]);
-          acc_chunk16<3>(a, b, r, acc, std::make_integer_sequence<int, 32>{});
+          acc_chunk16<3>(a, b, r2, acc, std::make_integer_sequence<int, 32>{});
         };
         if (it.w == 0) run(a0, b0); else run(a1, b1);
       } else {
@@ -346,6 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tc(const AttnParams p) {
 #pragma unroll
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) p.partial[((size_t)it.window() * p.way + it.c) * 4 + quad] = acc;
+      if (threadIdx.x == 256) TRACE(2, f, 2);
       ++f; it.next();
     }
   }
@@ -367,7 +396,7 @@ __global__ void __launch_bounds__(256) k_prep_k_img(const float *__restrict__ G,
   const float4 be = *reinterpret_cast<const float4 *>(ln_b + d0);
   for (int r = warp; r < TILE; r += 8) {
     uint2 packed = make_uint2(0u, 0u);
-    if (r < N) {
+    if (r < N && tuples[r * c] >= 0) {
       float4 k = make_float4(0, 0, 0, 0);
       for (int pp = 0; pp < c; ++pp) {
         const int fr = tuples[r * c + pp];
@@ -391,6 +420,11 @@ __global__ void __launch_bounds__(256) k_prep_k_img(const float *__restrict__ G,
 }
 
 // Support V^T image: rows = d, cols = support tuple s (zero for s >= N); from fp32 vs (way, N, D).
+__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+template <bool BF16>
 __global__ void __launch_bounds__(256) k_prep_vct_img(const float *__restrict__ vs, __half *__restrict__ img, int N) {
   const size_t cls = blockIdx.x;
   const float *v = vs + cls * (size_t)N * DD;
@@ -404,7 +438,11 @@ __global__ void __launch_bounds__(256) k_prep_vct_img(const float *__restrict__ 
       x[i] = s < N ? v[(size_t)s * DD + d] : 0.f;
     }
     uint4 pk;
-    pk.x = pack_half2(x[0], x[1]); pk.y = pack_half2(x[2], x[3]); pk.z = pack_half2(x[4], x[5]); pk.w = pack_half2(x[6], x[7]);
+    if constexpr (BF16) {
+      pk.x = pack_bf162(x[0], x[1]); pk.y = pack_bf162(x[2], x[3]); pk.z = pack_bf162(x[4], x[5]); pk.w = pack_bf162(x[6], x[7]);
+    } else {
+      pk.x = pack_half2(x[0], x[1]); pk.y = pack_half2(x[2], x[3]); pk.z = pack_half2(x[4], x[5]); pk.w = pack_half2(x[6], x[7]);
+    }
     const int s0 = sc * 8;
     *reinterpret_cast<uint4 *>(out + (s0 >> 6) * SUB_BYTES + sw128_offset(d, s0 & 63)) = pk;
   }
@@ -468,20 +506,32 @@ struct HeadParams {
   int n_win, way, N, T, ldg, voff, L, y_nk;
 };
 
-template <int Q2> __device__ __forceinline__ void diff_pair16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64]) {
-  constexpr int Q = 2 * Q2;
-  float d0 = 0.f, d1 = 0.f;
-  if constexpr (Q < 120) { constexpr int I = pair_i(Q, 16), J = pair_j(Q, 16); d0 = (a[I] + b[J]) - __uint_as_float(r[Q & 31]); }
-  if constexpr (Q + 1 < 120) { constexpr int I = pair_i(Q + 1, 16), J = pair_j(Q + 1, 16); d1 = (a[I] + b[J]) - __uint_as_float(r[(Q + 1) & 31]); }
-  pk[Q2] = pack_half2(d0, d1);
-}
-template <int CH, int... Js>
-__device__ __forceinline__ void diff_chunk16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64],
-                                             std::integer_sequence<int, Js...>) {
-  (diff_pair16<CH * 16 + Js>(a, b, r, pk), ...);
+// lexicographic rank of every slot of the padded-triangular query order (-1 = pad); filled by arx_tc_head_features
+__constant__ short c_slot_rank[128];
+
+template <int... Is> __device__ __forceinline__ void zero_pad_slots(uint32_t (&r)[4][32], std::integer_sequence<int, Is...>) {
+  ((r[arx_slot_row_start(2 * Is) >> 5][arx_slot_row_start(2 * Is) & 31] = 0u), ...);   // the pad slot of every even row
 }
 
-template <int MODE, int L>
+template <bool SLOT, int Q> struct TupleOf {   // (i, j) of column Q in the kernel's query-tuple order; valid == not a pad
+  static constexpr int i = SLOT ? arx_slot_i(Q) : pair_i(Q < 120 ? Q : 0, 16);
+  static constexpr int j = SLOT ? arx_slot_j(Q) : pair_j(Q < 120 ? Q : 0, 16);
+  static constexpr bool valid = SLOT ? (arx_slot_j(Q) != arx_slot_i(Q)) : (Q < 120);
+};
+template <bool SLOT, int Q2> __device__ __forceinline__ void diff_pair16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64]) {
+  constexpr int Q = 2 * Q2;
+  float d0 = 0.f, d1 = 0.f;
+  if constexpr (TupleOf<SLOT, Q>::valid) d0 = (a[TupleOf<SLOT, Q>::i] + b[TupleOf<SLOT, Q>::j]) - __uint_as_float(r[Q & 31]);
+  if constexpr (TupleOf<SLOT, Q + 1>::valid) d1 = (a[TupleOf<SLOT, Q + 1>::i] + b[TupleOf<SLOT, Q + 1>::j]) - __uint_as_float(r[(Q + 1) & 31]);
+  pk[Q2] = pack_half2(d0, d1);
+}
+template <bool SLOT, int CH, int... Js>
+__device__ __forceinline__ void diff_chunk16(const float (&a)[16], const float (&b)[16], const uint32_t (&r)[32], uint32_t (&pk)[64],
+                                             std::integer_sequence<int, Js...>) {
+  (diff_pair16<SLOT, CH * 16 + Js>(a, b, r, pk), ...);
+}
+
+template <int MODE, int L, bool SLOT>
 __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -602,16 +652,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bars[HB_S_EMPTY + sa]);
-      float z = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float e = fast_exp2(__uint_as_float(r[ch][j]));
-          r[ch][j] = __float_as_uint(e);
-          z += (ch * 32 + j < p.N) ? e : 0.f;
+        for (int j = 0; j < 32; ++j) r[ch][j] = ex2_bits(r[ch][j]);
+      }
+      if constexpr (SLOT) {
+        zero_pad_slots(r, std::make_integer_sequence<int, 8>{});
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[ch][j] = (ch * 32 + j < p.N) ? r[ch][j] : 0u;
         }
       }
+      float zp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zp[j & 3] += __uint_as_float(r[ch][j]);
+      }
+      const float z = (zp[0] + zp[1]) + (zp[2] + zp[3]);
       const float zinv = 1.0f / z;
       mbar_wait(&bars[HB_P_EMPTY], (t & 1) ^ 1);
 #pragma unroll
@@ -647,15 +708,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
         mbar_wait(&bars[HB_O_FULL], t & 1);
         tc_fence_after();
         tmem_ld32(TM_O + lane_base + 0, r); tmem_ld_wait();
-        diff_chunk16<0>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        diff_chunk16<SLOT, 0>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
         tmem_ld32(TM_O + lane_base + 32, r); tmem_ld_wait();
-        diff_chunk16<1>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        diff_chunk16<SLOT, 1>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
         tmem_ld32(TM_O + lane_base + 64, r); tmem_ld_wait();
-        diff_chunk16<2>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        diff_chunk16<SLOT, 2>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
         tmem_ld32(TM_O + lane_base + 96, r); tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bars[HB_O_EMPTY]);
-        diff_chunk16<3>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
+        diff_chunk16<SLOT, 3>(a, bb, r, pk, std::make_integer_sequence<int, 16>{});
       } else {
         const float *vq = p.Vq + (size_t)b * p.N * DD + d;
         mbar_wait(&bars[HB_O_FULL], t & 1);
@@ -694,8 +755,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bars[HB_Y_EMPTY]);
-      const int q = d;    // lane index doubles as the query tuple for the Y tile
-      if (q < p.N && p.y_img) {
+      // the lane index doubles as the query-tuple slot of the Y tile; y is indexed by the LEXICOGRAPHIC rank
+      // (the order of the reference's reshape, model.py:197, that fc1's weights expect)
+      int q = d;
+      bool qok = q < p.N;
+      if constexpr (SLOT) {
+        q = c_slot_rank[d];          // lexicographic rank of this slot, -1 for a pad
+        qok = q >= 0;
+      }
+      if (qok && p.y_img) {
         const int col = q * L;
         uint8_t *dst = reinterpret_cast<uint8_t *>(p.y_img) + ((size_t)(b >> 7) * p.y_nk + (col >> 6)) * (128 * 128);
 #pragma unroll
@@ -707,7 +775,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_head_tc(const HeadParams p) {
           pk.w = pack_half2(__uint_as_float(yv[l + 6]) + bias[l + 6], __uint_as_float(yv[l + 7]) + bias[l + 7]);
           *reinterpret_cast<uint4 *>(dst + sw128_offset(b & 127, (col & 63) + l)) = pk;
         }
-      } else if (q < p.N) {
+      } else if (qok) {
         float *dst = p.y + ((size_t)b * p.N + q) * L;
 #pragma unroll
         for (int l = 0; l < L; l += 4)
@@ -749,14 +817,33 @@ int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t
   }
   k_prep_kc_img<<<way, 256, 0, st>>>(tr.ks, tr.ks_img, tr.N);
   ARX_LAUNCH_CHECK(h);
-  k_prep_vct_img<<<way, 256, 0, st>>>(tr.vs, tr.vs_img, tr.N);
+  k_prep_vct_img<false><<<way, 256, 0, st>>>(tr.vs, tr.vs_img, tr.N);
+  ARX_LAUNCH_CHECK(h);
+  if (!tr.vs_img_bf) ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.vs_img_bf), (size_t)h->way_cap * IMG_BYTES));
+  k_prep_vct_img<true><<<way, 256, 0, st>>>(tr.vs, tr.vs_img_bf, tr.N);      // bf16 copy for the second-generation kernel
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }
 
-int arx_tc_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, cudaStream_t st) {
+bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr) {
+  return h->T == 16 && tr.c == 2 && (h->tc_variant & 8) == 0;
+}
+
+int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st) {
   const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
-  k_prep_k_img<<<(unsigned)n_win, 256, 0, st>>>(G, tr.tuples, tr.ln_g, tr.ln_b, kq_img, h->T, tr.c, tr.N, 2 * tr.c * h->D, alpha);
+  const int32_t *table = tr.tuples;
+  int rows = tr.N;
+  if (slot_order) {
+    if (!tr.q_slots) {
+      int32_t host[256];
+      arx_tc2_slot_table(host);
+      ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.q_slots), sizeof(host)));
+      ARX_CUDA(h, cudaMemcpy(tr.q_slots, host, sizeof(host), cudaMemcpyHostToDevice));
+    }
+    table = tr.q_slots;
+    rows = 128;
+  }
+  k_prep_k_img<<<(unsigned)n_win, 256, 0, st>>>(G, table, tr.ln_g, tr.ln_b, kq_img, h->T, tr.c, rows, 2 * tr.c * h->D, alpha);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }
@@ -766,8 +853,16 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
   AttnParams p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.G = G; p.Vq = Vq; p.partial = partial;
   p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = 2 * tr.c * h->D; p.voff = tr.c * h->D;
+  p.trace = h->trace_buf;
   const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_attention: generic epilogue needs Vq");
+  if (mode0 && arx_tc_slot_order(h, tr)) {
+    int rc = arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, st);
+    if (rc) return rc;
+    k_finish_tc<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
+    ARX_LAUNCH_CHECK(h);
+    return ARX_OK;
+  }
   const int groups = (int)((n_win + GROUP - 1) / GROUP);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
   const bool p_mn = (variant & 1) == 0;     // variant bit 0: use the K-major P layout (2-byte stores) instead of MN-major
@@ -803,8 +898,19 @@ int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *
   const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_head: generic epilogue needs Vq");
   void (*kern)(const HeadParams) = nullptr;
-  if (h->T == 16) kern = mode0 ? k_head_tc<0, 16> : k_head_tc<1, 16>;
-  else if (h->T == 32) kern = k_head_tc<1, 32>;
+  const bool slot = mode0 && arx_tc_slot_order(h, tr);
+  static bool rank_table_set = false;
+  if (slot && !rank_table_set) {
+    short host[128];
+    for (int q = 0; q < 128; ++q) {
+      const int i = arx_slot_i(q), j = arx_slot_j(q);
+      host[q] = (j == i) ? (short)-1 : (short)(i * (2 * 16 - i - 1) / 2 + (j - i - 1));
+    }
+    ARX_CUDA(h, cudaMemcpyToSymbol(c_slot_rank, host, sizeof(host)));
+    rank_table_set = true;
+  }
+  if (h->T == 16) kern = mode0 ? (slot ? k_head_tc<0, 16, true> : k_head_tc<0, 16, false>) : k_head_tc<1, 16, false>;
+  else if (h->T == 32) kern = k_head_tc<1, 32, false>;
   else return arx_fail(h, ARX_ERR_INVALID, "tc_head: unsupported seq_len");
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
   ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H_SMEM_BYTES));

@@ -67,6 +67,7 @@ def main():
       "attn-fp16, frames-fp32": dict(mlp_a="fp32", mlp_w="fp32", proj_a="fp32", proj_w="fp32", qk="fp16", pv="fp16", disc="fp16"),
       "attn-fp16, frames-fp16x2": dict(mlp_a="fp16x2", mlp_w="fp16x2", proj_a="fp16x2", proj_w="fp16x2", qk="fp16", pv="fp16", disc="fp16"),
       "attn-bf16, frames-fp32": dict(mlp_a="fp32", mlp_w="fp32", proj_a="fp32", proj_w="fp32", qk="bf16", pv="bf16", disc="bf16"),
+      "all-fp16 but PV bf16":   dict(mlp_a="fp16", mlp_w="fp16", proj_a="fp16", proj_w="fp16", qk="fp16", pv="bf16", disc="fp16"),
       "attn-fp16, mlp-fp16 proj-fp32": dict(mlp_a="fp16", mlp_w="fp16", proj_a="fp32", proj_w="fp32", qk="fp16", pv="fp16", disc="fp16"),
       "attn-fp16, mlp-fp32 proj-fp16": dict(mlp_a="fp32", mlp_w="fp32", proj_a="fp16", proj_w="fp16", qk="fp16", pv="fp16", disc="fp16"),
     }
