@@ -25,13 +25,11 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def broadcast_support(scorer, way: int, src: int = 0, group=None, device=None) -> None:
-    """Rank `src` has called set_support; every other rank receives the operands."""
+    """Rank `src` has called set_support for `way` classes; every other rank receives the operands.
+    `way` must be passed identically on every rank (no metadata exchange, no host synchronisation)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     rank = dist.get_rank(group)
-    meta = torch.tensor([way if rank == src else 0], dtype=torch.int64, device=device)
-    dist.broadcast(meta, src=src, group=group)
-    way = int(meta.item())
     if rank == src:
         blob = scorer.export_support()
     else:
@@ -42,24 +40,28 @@ def broadcast_support(scorer, way: int, src: int = 0, group=None, device=None) -
 
 
 def gather_scores(logits: torch.Tensor, is_true, n_total: int, group=None):
-    """All-gather the per-rank `[logits | is_true]` rows (ragged shards padded to the largest)."""
+    """All-gather the per-rank `[logits | is_true]` rows: one collective per batch.  Equal shards are gathered
+    straight into the result; ragged shards are padded to the largest and trimmed."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return logits, is_true
     world = dist.get_world_size(group)
     way = logits.shape[1]
     cols = way + (1 if is_true is not None else 0)
     mx = shard_bounds(n_total, world, 0)[1]
-    packed = torch.zeros((mx, cols), dtype=torch.float32, device=logits.device)
+    even = n_total % world == 0
+    packed = torch.empty((mx, cols), dtype=torch.float32, device=logits.device)
+    if not even:
+        packed.zero_()
     packed[: logits.shape[0], :way] = logits
     if is_true is not None:
         packed[: logits.shape[0], way:] = is_true
-    out = torch.empty((world, mx, cols), dtype=torch.float32, device=logits.device)
-    dist.all_gather_into_tensor(out.view(world * mx, cols), packed, group=group)
-    parts = []
-    for r in range(world):
-        s, e = shard_bounds(n_total, world, r)
-        parts.append(out[r, : e - s])
-    full = torch.cat(parts)
+    out = torch.empty((world * mx, cols), dtype=torch.float32, device=logits.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    if even:
+        full = out
+    else:
+        out3 = out.view(world, mx, cols)
+        full = torch.cat([out3[r, : shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0]] for r in range(world)])
     return full[:, :way], (full[:, way:] if is_true is not None else None)
 
 
