@@ -490,6 +490,10 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const bool tc_head = use_tc && disc && arx_tc_head_supported(h, tr) && (h->tc_variant & 2) == 0;
   const bool tuples32 = !use_tc || (disc && !tc_head) || !mode0;    // fp32 tuple tensors: fp32 path/head pass, generic epilogue
   const bool tcl = use_tc && h->tc_linears && (h->tc_variant & 4) == 0;
+  // fused projection epilogue (Kq images + compact V projections): T=16 pairs, slot order, no fp32 tuple tensors needed
+  const bool fused_proj = tcl && mode0 && arx_tc_slot_order(h, tr) && !tuples32 && (h->tc_variant & 16) == 0;
+  const int g_ld = fused_proj ? 2 * h->D : 2 * tr.c * h->D;      // row stride of G as the attention epilogues see it
+  const int g_voff = fused_proj ? 0 : tr.c * h->D;
   const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32, tcl, tc_head);
   Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32, tcl, tc_head);
   size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
@@ -514,7 +518,13 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, tr.tl_proj.nk, st))) return rc;
       }
       if ((rc = prof_mark(h, 1, st))) return rc;
-      if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, rows, w.G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
+      if (fused_proj) {
+        int32_t slots[256];
+        arx_tc2_slot_table(slots);
+        const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
+        if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G, tr.bp, 2 * tr.c * h->D, st)))
+          return rc;
+      } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, rows, w.G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
     } else {
       if (from_frames) {
         if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, rows, w.H1, w.FE, st))) return rc;
@@ -527,17 +537,17 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     }
     if ((rc = prof_mark(h, 2, st))) return rc;
     if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
-    if (use_tc && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
+    if (use_tc && !fused_proj && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
     if (use_tc) {
       if ((rc = arx_tc_attention(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, w.partial, logits_dev + b0 * way, ch,
-                                 h->tc_variant, st)))
+                                 h->tc_variant, g_ld, g_voff, st)))
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
       if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
-                                                        h->tl_d1.nk, st)))
+                                                        h->tl_d1.nk, g_ld, g_voff, st)))
         return rc;
       if (disc && !tc_head && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
     } else {

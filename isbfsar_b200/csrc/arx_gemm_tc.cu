@@ -16,7 +16,10 @@ using namespace ptx;
 constexpr uint32_t A_SUB = 128 * 128;       // 128 rows x 64 fp16
 constexpr int G_THREADS = 192;
 
-enum { OUT_IMG16 = 0, OUT_F32 = 1, OUT_SIGMOID_DOT = 2 };
+enum { OUT_IMG16 = 0, OUT_F32 = 1, OUT_SIGMOID_DOT = 2, OUT_PROJ16 = 3 };
+
+// internal slot order of the query tuples for the fused projection epilogue (frame pairs, -1 = pad)
+__constant__ int c_qslots[256];
 
 struct GemmParams {
   const __half *a_img;     // [m_tiles][nk][128 x 64]
@@ -36,6 +39,12 @@ struct GemmParams {
   // OUT_SIGMOID_DOT
   const float *w3, *b3;    // [BN], [1]
   float *out1;             // [M]
+  // OUT_PROJ16 (T=16 pair tuples): column tile 0 = K parts -> tuple gather + LayerNorm -> Kq images;
+  // column tile 1 = V parts -> fp32 [M][256]
+  __half *kq_img;          // [M/16] window images of 32 KB
+  const float *ln_g, *ln_b;
+  float alpha;
+  int table_ld;
 };
 
 template <int BN, int OUT>
@@ -96,6 +105,101 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
     mbar_wait(&bars[4], 0);
     tc_fence_after();
     float dot = 0.f;
+    if constexpr (OUT == OUT_PROJ16) {
+      if (nt == 0) {
+        // ---- K parts: this warp owns rows 32w..32w+31 = two whole windows of 16 frames.  Per window: stage the
+        // 16 x 256 fp32 frame projections in shared memory (the operand stages are idle now), then build the
+        // 128 tuple rows K = LN(Gk1[i] + Gk2[j]) * alpha -> fp16 -> swizzled Kq image  (model.py:69-82).
+        float *ws = reinterpret_cast<float *>(smem + warp * 16384);
+        const int d0 = lane * 4;
+        const float4 g = *reinterpret_cast<const float4 *>(p.ln_g + d0);
+        const float4 be = *reinterpret_cast<const float4 *>(p.ln_b + d0);
+        for (int wi = 0; wi < 2; ++wi) {
+          const int64_t win = (int64_t)mt * 8 + warp * 2 + wi;
+          __syncwarp();
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_base + c0, v);
+            tmem_ld_wait();
+            if ((lane >> 4) == wi) {
+              const float *tb = p.table + (int64_t)(lane & 15) * p.table_ld + c0;
+              float *dst = ws + (lane & 15) * 256 + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 tv = __ldg(reinterpret_cast<const float4 *>(tb + j));
+                *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) + tv.x, __uint_as_float(v[j + 1]) + tv.y,
+                                                                   __uint_as_float(v[j + 2]) + tv.z, __uint_as_float(v[j + 3]) + tv.w);
+              }
+            }
+          }
+          __syncwarp();
+          if (win * 16 < p.M) {
+            uint8_t *out = reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768;
+            // four tuple rows per iteration: their LayerNorm reductions (10 dependent shuffles each) interleave
+#pragma unroll 1
+            for (int s4 = 0; s4 < 128; s4 += 4) {
+              float4 k[4];
+              float sum[4], q[4];
+              bool ok[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int fi = c_qslots[2 * (s4 + u)], fj = c_qslots[2 * (s4 + u) + 1];
+                ok[u] = fi >= 0;
+                const float4 a = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fi : 0) * 256 + d0);
+                const float4 b = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fj : 0) * 256 + 128 + d0);
+                k[u] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+                sum[u] = (k[u].x + k[u].y) + (k[u].z + k[u].w);
+              }
+#pragma unroll
+              for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float mean = sum[u] * (1.0f / 128.0f);
+                k[u] = make_float4(k[u].x - mean, k[u].y - mean, k[u].z - mean, k[u].w - mean);
+                q[u] = k[u].x * k[u].x + k[u].y * k[u].y + k[u].z * k[u].z + k[u].w * k[u].w;
+              }
+#pragma unroll
+              for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float rstd = 1.0f / sqrtf(q[u] * (1.0f / 128.0f) + 1e-5f);
+                __half2 h0 = __floats2half2_rn((k[u].x * rstd * g.x + be.x) * p.alpha, (k[u].y * rstd * g.y + be.y) * p.alpha);
+                __half2 h1 = __floats2half2_rn((k[u].z * rstd * g.z + be.z) * p.alpha, (k[u].w * rstd * g.w + be.w) * p.alpha);
+                uint2 packed;
+                packed.x = ok[u] ? *reinterpret_cast<uint32_t *>(&h0) : 0u;
+                packed.y = ok[u] ? *reinterpret_cast<uint32_t *>(&h1) : 0u;
+                *reinterpret_cast<uint2 *>(out + (d0 >> 6) * 16384 + sw128_offset(s4 + u, d0 & 63)) = packed;
+              }
+            }
+          }
+        }
+      } else {
+        // ---- V parts: fp32 [M][256] (bias and positional-encoding table folded in), read by the attention epilogues
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_base + c0, v);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float *dst = p.c + row * 256 + c0;
+            const float *tb = p.table + (int64_t)(row % p.T) * p.table_ld + 256 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 tv = __ldg(reinterpret_cast<const float4 *>(tb + j));
+              *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) + tv.x, __uint_as_float(v[j + 1]) + tv.y,
+                                                                 __uint_as_float(v[j + 2]) + tv.z, __uint_as_float(v[j + 3]) + tv.w);
+            }
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -141,6 +245,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) dot = fmaf(x[j], __ldg(p.w3 + col0 + j), dot);
       }
+    }
     }
     if constexpr (OUT == OUT_SIGMOID_DOT) {
       if (row < p.M) p.out1[row] = 1.f / (1.f + expf(-(dot + __ldg(p.b3))));
@@ -260,4 +365,20 @@ int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half 
   p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.M = M; p.act = ARX_ACT_RELU; p.w3 = w3; p.b3 = b3; p.out1 = out;
   if (L.BN == 64) return launch_gemm<64, OUT_SIGMOID_DOT>(h, p, 1, st);
   return arx_fail(h, ARX_ERR_INVALID, "tc_linear_sigmoid_dot: unsupported BN %d", L.BN);
+}
+
+// Fused K/V projection for T=16 pair tuples: Kq images (tuple gather + LayerNorm + scale, internal slot order)
+// and the fp32 V projections [M][256], straight from the GEMM accumulator -- no `G` round trip.
+int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
+                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, cudaStream_t st) {
+  if (L.BN != 256 || L.n_tiles != 2) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: needs a 512-column projection");
+  static bool slots_set = false;
+  if (!slots_set) {
+    ARX_CUDA(h, cudaMemcpyToSymbol(c_qslots, slots_host, 256 * sizeof(int)));
+    slots_set = true;
+  }
+  GemmParams p{};
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;
+  p.kq_img = kq_img; p.ln_g = ln_g; p.ln_b = ln_b; p.alpha = alpha; p.table_ld = table_ld;
+  return launch_gemm<256, OUT_PROJ16>(h, p, 2, st);
 }

@@ -120,12 +120,12 @@ int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t
 int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st);
 bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, cudaStream_t st);
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, cudaStream_t st);
 
 bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st);
 int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, cudaStream_t st);
+                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, int g_ld, int g_voff, cudaStream_t st);
 
 // ---- tcgen05 GEMM (arx_gemm_tc.cu) ------------------------------------------------
 int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw, const float *bias, int N, int K, int BN, cudaStream_t st);
@@ -157,7 +157,10 @@ static_assert(arx_slot_row_start(16) == 128, "slot layout must fill the 128-colu
 
 void arx_tc2_slot_table(int32_t *out /* 256 */);
 int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, cudaStream_t st);
+                             float *partial, int g_ld, int g_voff, cudaStream_t st);
+
+int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
+                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

@@ -849,15 +849,15 @@ int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t
 }
 
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, cudaStream_t st) {
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, cudaStream_t st) {
   AttnParams p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.G = G; p.Vq = Vq; p.partial = partial;
-  p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = 2 * tr.c * h->D; p.voff = tr.c * h->D;
+  p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = g_ld; p.voff = g_voff;
   p.trace = h->trace_buf;
   const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_attention: generic epilogue needs Vq");
   if (mode0 && arx_tc_slot_order(h, tr)) {
-    int rc = arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, st);
+    int rc = arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st);
     if (rc) return rc;
     k_finish_tc<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
     ARX_LAUNCH_CHECK(h);
@@ -889,11 +889,11 @@ int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st) {
 
 // y (n_win, N*T) fp32 = dimensionality_reduction(diff of the winning class), computed on tensor cores
 int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, cudaStream_t st) {
+                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, int g_ld, int g_voff, cudaStream_t st) {
   HeadParams p{};
   p.y_img = y_img; p.y_nk = y_nk;
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.wdr_img = h->wdr_img; p.G = G; p.Vq = Vq; p.dr_b = h->dr_b;
-  p.chosen = chosen; p.y = y; p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = 2 * tr.c * h->D; p.voff = tr.c * h->D;
+  p.chosen = chosen; p.y = y; p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = g_ld; p.voff = g_voff;
   p.L = h->T;
   const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_head: generic epilogue needs Vq");

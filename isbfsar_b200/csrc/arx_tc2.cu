@@ -353,10 +353,10 @@ void arx_tc2_slot_table(int32_t *out /* 256 */) {
 }
 
 int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, cudaStream_t st) {
+                             float *partial, int g_ld, int g_voff, cudaStream_t st) {
   Attn2Params p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img_bf; p.G = G; p.partial = partial;
-  p.n_win = (int)n_win; p.way = way; p.ldg = 2 * tr.c * h->D; p.voff = tr.c * h->D; p.trace = h->trace_buf;
+  p.n_win = (int)n_win; p.way = way; p.ldg = g_ld; p.voff = g_voff; p.trace = h->trace_buf;
   const int groups = (int)((n_win + GROUP - 1) / GROUP);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
   ARX_CUDA(h, cudaFuncSetAttribute(k_attn_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
