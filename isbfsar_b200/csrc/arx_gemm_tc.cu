@@ -136,14 +136,15 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
           __syncwarp();
           if (win * 16 < p.M) {
             uint8_t *out = reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768;
-            // four tuple rows per iteration: their LayerNorm reductions (10 dependent shuffles each) interleave
+            // NU tuple rows per iteration: their LayerNorm reductions (10 dependent shuffles each) interleave
+            constexpr int NU = 8;
 #pragma unroll 1
-            for (int s4 = 0; s4 < 128; s4 += 4) {
-              float4 k[4];
-              float sum[4], q[4];
-              bool ok[4];
+            for (int s4 = 0; s4 < 128; s4 += NU) {
+              float4 k[NU];
+              float sum[NU], q[NU];
+              bool ok[NU];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < NU; ++u) {
                 const int fi = c_qslots[2 * (s4 + u)], fj = c_qslots[2 * (s4 + u) + 1];
                 ok[u] = fi >= 0;
                 const float4 a = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fi : 0) * 256 + d0);
@@ -154,10 +155,10 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 #pragma unroll
               for (int o = 16; o; o >>= 1) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+                for (int u = 0; u < NU; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < NU; ++u) {
                 const float mean = sum[u] * (1.0f / 128.0f);
                 k[u] = make_float4(k[u].x - mean, k[u].y - mean, k[u].z - mean, k[u].w - mean);
                 q[u] = k[u].x * k[u].x + k[u].y * k[u].y + k[u].z * k[u].z + k[u].w * k[u].w;
@@ -165,10 +166,10 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 #pragma unroll
               for (int o = 16; o; o >>= 1) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+                for (int u = 0; u < NU; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < NU; ++u) {
                 const float rstd = 1.0f / sqrtf(q[u] * (1.0f / 128.0f) + 1e-5f);
                 __half2 h0 = __floats2half2_rn((k[u].x * rstd * g.x + be.x) * p.alpha, (k[u].y * rstd * g.y + be.y) * p.alpha);
                 __half2 h1 = __floats2half2_rn((k[u].z * rstd * g.z + be.z) * p.alpha, (k[u].w * rstd * g.w + be.w) * p.alpha);

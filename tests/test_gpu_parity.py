@@ -271,3 +271,106 @@ def test_errors_are_loud():
     cpu_model = TRXOS(Args(cfg))
     with pytest.raises(RuntimeError):
         cpu_model({"sk": torch.zeros(1, 5, 16, 90)}, torch.arange(5)[None], {"sk": torch.zeros(1, 16, 90)})
+
+
+@pytest.mark.parametrize("B", [1, 3, 129, 257])
+@pytest.mark.parametrize("way", [1, 2, 7])
+def test_ragged_batches_and_odd_ways(B, way):
+    """Tail handling of the persistent kernels: odd window counts (groups of 2), odd class counts."""
+    cfg = Cfg(way=way)
+    m, sd = make_model(cfg, 0)
+    support, labels, query, planted = make_episode(cfg, B, 51 + B + way, "structured")
+    o = TrxOracle(cfg, sd)
+    lo, it = o.score(support, labels, query)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2
+    assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), lo.argmax(1))
+
+
+def test_cfg3_60way_at_scale():
+    """BASELINE cfg3 shape on one GPU: 60-way support, a rank's shard of the 65 536 windows (8192)."""
+    cfg = Cfg(way=60)
+    m, sd = make_model(cfg, 0)
+    B = 8192
+    support, labels, query, planted = make_episode(cfg, B, 61, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2 and logits.shape == (B, 60)
+    assert (logits.argmax(1).cpu().numpy() == planted).all()
+    o = TrxOracle(cfg, sd)
+    idx = np.r_[0:16, B - 16:B]
+    lo, it = o.score(support, labels, query[idx], chunk=16)
+    assert rel_err(logits[idx].cpu(), lo).max() < TOL_TC and rel_err(is_true[idx].cpu(), it).max() < TOL_TC
+
+
+def test_cfg5_heatmaps_to_scores_end_to_end(golden_dir):
+    """BASELINE cfg5: 1024 synthetic heatmap frames -> decode kernel -> 1009 sliding windows -> AR scoring."""
+    from isbfsar_b200 import HeatmapDecoder
+    from oracle import decode_oracle as D
+    g = np.load(os.path.join(golden_dir, "decode_64.npz"))
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    hm = make_heatmaps(1024, seed=2)
+    dec = HeatmapDecoder(m, g["expand30"], None, g["new_K"], g["homo_inv"])
+    poses, valid = dec.decode(torch.from_numpy(hm).cuda())
+    assert valid.all()
+    ref_poses, ref_valid = D.decode_frames(hm[:96], g["expand30"], np.arange(30), g["new_K"], g["homo_inv"])
+    assert np.abs(poses[:96].cpu().numpy() - ref_poses).max() < 1e-4 * np.abs(ref_poses).max()
+    windows = poses.unfold(0, 16, 1).permute(0, 2, 1).contiguous()            # (1009, 16, 90) sliding windows
+    assert windows.shape == (1009, 16, 90)
+    support = windows[[0, 200, 400, 600, 800]].clone()                          # 5 of the windows act as the support set
+    m.set_support(poses=support)
+    logits, is_true = m.score(windows)
+    assert (logits[[0, 200, 400, 600, 800]].argmax(1).cpu() == torch.arange(5)).all()
+    # oracle on the oracle-decoded poses of the first 80 windows (decode error 1e-4 of scale feeds through)
+    o = TrxOracle(cfg, sd)
+    ref_w = np.stack([ref_poses[i:i + 16] for i in range(80)]).astype(np.float32)
+    lo, it = o.score(support.cpu().numpy()[None], np.arange(5)[None], ref_w)
+    assert rel_err(logits[:80].cpu(), lo).max() < 5e-3
+    assert np.array_equal(logits[:80].argmax(1).cpu().numpy(), lo.argmax(1))
+
+
+def test_large_layernorm_affine_falls_back_to_fp32_kernels():
+    """exp2 without max-subtraction is only used inside the static LayerNorm bound; beyond it the
+    fp32 kernels with an online max take over -- results stay within tolerance."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    with torch.no_grad():
+        m.transformers[0].norm_k.weight.fill_(3.0)
+    sd = dict(sd)
+    sd["transformers.0.norm_k.weight"] = np.full((128,), 3.0, np.float32)
+    support, labels, query, _ = make_episode(cfg, 64, 71, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 1
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query)
+    assert rel_err(logits.cpu(), lo).max() < 1e-3 and rel_err(is_true.cpu(), it).max() < 1e-3
+
+
+def test_t8_runs_on_generic_tensor_core_kernels():
+    """T=8 pairs (N=28): first-generation tcgen05 kernel with the generic epilogue; fp32 open-set head."""
+    cfg = Cfg(seq_len=8)
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 130, 81, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query)
+    assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
+
+
+@pytest.mark.parametrize("variant", [8, 8 + 1, 8 + 2, 4, 16])
+def test_kernel_variants_agree(variant):
+    """Bring-up variants stay green: first-generation attention kernel (8), its K-major P layout (+1), fp32
+    open-set head (+2), fp32 linear layers (4), unfused projection (16)."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 131, 91, "structured")
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    m.debug_set(0, variant)
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2
+    assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
