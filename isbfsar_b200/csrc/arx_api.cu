@@ -189,6 +189,7 @@ int arx_create(const arx_config *cfg, arx_handle **out) {
     A(&tr.pe, (size_t)h->T * h->F);
     A(&tr.wp, (size_t)2 * tr.c * h->D * h->F);
     A(&tr.bp, (size_t)h->T * 2 * tr.c * h->D);
+    A(&tr.bp_sums, (size_t)h->T * 2);
     A(&tr.ln_g, h->D); A(&tr.ln_b, h->D);
     if (rc == ARX_OK) rc = dev_alloc(h, &tr.tuples, (size_t)tr.N * tr.c);
     if (rc == ARX_OK) rc = arx_build_tuple_table(h, h->T, tr.c, tr.N, tr.tuples, 0);
@@ -217,7 +218,7 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->fc1_w); cudaFree(h->fc1_b); cudaFree(h->fc2_w); cudaFree(h->fc2_b);
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     ArxTransformer &tr = h->tr[i];
-    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots);
+    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots); cudaFree(tr.bp_sums);
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
@@ -299,7 +300,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     }
     if (h->cfg.has_discriminator) {
       const int K1 = h->T * (h->T - 1) / 2 * h->T;
-      if ((rc = arx_tc_linear_prepare(h, h->tl_d1, h->d1_w, K1, h->d1_b, 256, K1, 256, st))) return rc;
+      if ((rc = arx_tc_linear_prepare(h, h->tl_d1, h->d1_w, K1, h->d1_b, 256, K1, 64, st))) return rc;
       if ((rc = arx_tc_linear_prepare(h, h->tl_d2, h->d2_w, 256, h->d2_b, 64, 256, 64, st))) return rc;
     }
     h->tc_linears = true;
@@ -522,7 +523,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         int32_t slots[256];
         arx_tc2_slot_table(slots);
         const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
-        if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G, tr.bp, 2 * tr.c * h->D, st)))
+        if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G, tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
           return rc;
       } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, rows, w.G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
     } else {

@@ -45,21 +45,22 @@ struct GemmParams {
   const float *ln_g, *ln_b;
   float alpha;
   int table_ld;
+  const float *table_sums; // [T][2]: row sums of the table over the two K parts
 };
 
-template <int BN, int OUT>
+template <int BN, int OUT, int NST>
 __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
   constexpr uint32_t B_SUB = BN * 128;
   constexpr uint32_t STAGE = A_SUB + B_SUB;
   constexpr uint32_t TM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);     // full[2], empty[2], acc
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE + 5 * 8);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * STAGE);     // full[NST], empty[NST], acc
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NST * STAGE + (2 * NST + 1) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
+    for (int i = 0; i < 2 * NST + 1; ++i) mbar_init(&bars[i], 1);
     mbar_init_fence();
   }
   if (warp == 5) { tmem_alloc(tmem_slot, TM_COLS); tmem_relinquish(); }
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
       const uint8_t *a = reinterpret_cast<const uint8_t *>(p.a_img) + (size_t)mt * p.nk * A_SUB;
       const uint8_t *w = reinterpret_cast<const uint8_t *>(p.w_img) + (size_t)nt * p.nk * B_SUB;
       for (int ks = 0; ks < p.nk; ++ks) {
-        const int st = ks & 1;
-        mbar_wait(&bars[2 + st], ((ks >> 1) & 1) ^ 1);
+        const int st = ks % NST;
+        mbar_wait(&bars[NST + st], ((ks / NST) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars[st], STAGE);
         bulk_g2s(smem + st * STAGE, a + (size_t)ks * A_SUB, A_SUB, &bars[st]);
         bulk_g2s(smem + st * STAGE + A_SUB, w + (size_t)ks * B_SUB, B_SUB, &bars[st]);
@@ -86,23 +87,23 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
       constexpr uint32_t IDESC = idesc_f16(128, BN, 0, 0);
       const uint32_t sbase = smem_u32(smem);
       for (int ks = 0; ks < p.nk; ++ks) {
-        const int st = ks & 1;
-        mbar_wait(&bars[st], (ks >> 1) & 1);
+        const int st = ks % NST;
+        mbar_wait(&bars[st], (ks / NST) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           mma_f16_ss(tmem, smem_desc_at(DESC_K, sbase + st * STAGE + kk * 32), smem_desc_at(DESC_K, sbase + st * STAGE + A_SUB + kk * 32),
                      IDESC, (ks | kk) != 0);
-        mma_commit(&bars[2 + st]);
+        mma_commit(&bars[NST + st]);
       }
-      mma_commit(&bars[4]);
+      mma_commit(&bars[2 * NST]);
     }
   } else {
     // epilogue: thread == row of the tile == TMEM lane
     const int r = warp * 32 + lane;
     const int64_t row = (int64_t)mt * 128 + r;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    mbar_wait(&bars[4], 0);
+    mbar_wait(&bars[2 * NST], 0);
     tc_fence_after();
     float dot = 0.f;
     if constexpr (OUT == OUT_PROJ16) {
@@ -112,8 +113,27 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
         // 128 tuple rows K = LN(Gk1[i] + Gk2[j]) * alpha -> fp16 -> swizzled Kq image  (model.py:69-82).
         float *ws = reinterpret_cast<float *>(smem + warp * 16384);
         const int d0 = lane * 4;
-        const float4 g = *reinterpret_cast<const float4 *>(p.ln_g + d0);
-        const float4 be = *reinterpret_cast<const float4 *>(p.ln_b + d0);
+        float4 g = *reinterpret_cast<const float4 *>(p.ln_g + d0);
+        float4 be = *reinterpret_cast<const float4 *>(p.ln_b + d0);
+        g.x *= p.alpha; g.y *= p.alpha; g.z *= p.alpha; g.w *= p.alpha;          // fold the exp2 pre-scale into the affine
+        be.x *= p.alpha; be.y *= p.alpha; be.z *= p.alpha; be.w *= p.alpha;
+        // LayerNorm mean by linearity: mean(A_i + B_j) = mean(A_i) + mean(B_j), and every lane holds one whole frame
+        // row in its registers while staging -- so the rows are stored CENTRED and a tuple needs one reduction only.
+        const float *tb = p.table + (int64_t)(lane & 15) * p.table_ld;
+        float sumA = __ldg(p.table_sums + (lane & 15) * 2), sumB = __ldg(p.table_sums + (lane & 15) * 2 + 1);   // row sums of the table
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_base + c0, v);
+          tmem_ld_wait();
+          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            t0 += __uint_as_float(v[j]); t1 += __uint_as_float(v[j + 1]); t2 += __uint_as_float(v[j + 2]); t3 += __uint_as_float(v[j + 3]);
+          }
+          if (c0 < 128) sumA += (t0 + t1) + (t2 + t3); else sumB += (t0 + t1) + (t2 + t3);
+        }
+        const float mA = sumA * (1.0f / 128.0f), mB = sumB * (1.0f / 128.0f);
         for (int wi = 0; wi < 2; ++wi) {
           const int64_t win = (int64_t)mt * 8 + warp * 2 + wi;
           __syncwarp();
@@ -121,27 +141,28 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + c0, v);
+            float4 tv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tv[j] = __ldg(reinterpret_cast<const float4 *>(tb + c0) + j);     // in flight with the TMEM load
             tmem_ld_wait();
             if ((lane >> 4) == wi) {
-              const float *tb = p.table + (int64_t)(lane & 15) * p.table_ld + c0;
+              const float m = c0 < 128 ? mA : mB;
               float *dst = ws + (lane & 15) * 256 + c0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 tv = __ldg(reinterpret_cast<const float4 *>(tb + j));
-                *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) + tv.x, __uint_as_float(v[j + 1]) + tv.y,
-                                                                   __uint_as_float(v[j + 2]) + tv.z, __uint_as_float(v[j + 3]) + tv.w);
-              }
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(v[4 * j]) + tv[j].x - m, __uint_as_float(v[4 * j + 1]) + tv[j].y - m,
+                                                                       __uint_as_float(v[4 * j + 2]) + tv[j].z - m, __uint_as_float(v[4 * j + 3]) + tv[j].w - m);
             }
           }
           __syncwarp();
           if (win * 16 < p.M) {
             uint8_t *out = reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768;
-            // NU tuple rows per iteration: their LayerNorm reductions (10 dependent shuffles each) interleave
+            // NU tuple rows per iteration so that their variance reductions (5 dependent shuffles each) interleave
             constexpr int NU = 8;
 #pragma unroll 1
             for (int s4 = 0; s4 < 128; s4 += NU) {
               float4 k[NU];
-              float sum[NU], q[NU];
+              float q[NU];
               bool ok[NU];
 #pragma unroll
               for (int u = 0; u < NU; ++u) {
@@ -149,18 +170,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
                 ok[u] = fi >= 0;
                 const float4 a = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fi : 0) * 256 + d0);
                 const float4 b = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fj : 0) * 256 + 128 + d0);
-                k[u] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-                sum[u] = (k[u].x + k[u].y) + (k[u].z + k[u].w);
-              }
-#pragma unroll
-              for (int o = 16; o; o >>= 1) {
-#pragma unroll
-                for (int u = 0; u < NU; ++u) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
-              }
-#pragma unroll
-              for (int u = 0; u < NU; ++u) {
-                const float mean = sum[u] * (1.0f / 128.0f);
-                k[u] = make_float4(k[u].x - mean, k[u].y - mean, k[u].z - mean, k[u].w - mean);
+                k[u] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);          // already zero-mean
                 q[u] = k[u].x * k[u].x + k[u].y * k[u].y + k[u].z * k[u].z + k[u].w * k[u].w;
               }
 #pragma unroll
@@ -170,9 +180,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
               }
 #pragma unroll
               for (int u = 0; u < NU; ++u) {
-                const float rstd = 1.0f / sqrtf(q[u] * (1.0f / 128.0f) + 1e-5f);
-                __half2 h0 = __floats2half2_rn((k[u].x * rstd * g.x + be.x) * p.alpha, (k[u].y * rstd * g.y + be.y) * p.alpha);
-                __half2 h1 = __floats2half2_rn((k[u].z * rstd * g.z + be.z) * p.alpha, (k[u].w * rstd * g.w + be.w) * p.alpha);
+                const float rstd = rsqrtf(q[u] * (1.0f / 128.0f) + 1e-5f);
+                __half2 h0 = __floats2half2_rn(fmaf(k[u].x * rstd, g.x, be.x), fmaf(k[u].y * rstd, g.y, be.y));
+                __half2 h1 = __floats2half2_rn(fmaf(k[u].z * rstd, g.z, be.z), fmaf(k[u].w * rstd, g.w, be.w));
                 uint2 packed;
                 packed.x = ok[u] ? *reinterpret_cast<uint32_t *>(&h0) : 0u;
                 packed.y = ok[u] ? *reinterpret_cast<uint32_t *>(&h1) : 0u;
@@ -187,16 +197,17 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_base + c0, v);
+          const float *tb = p.table + (int64_t)(row % p.T) * p.table_ld + 256 + c0;
+          float4 tv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) tv[j] = __ldg(reinterpret_cast<const float4 *>(tb) + j);
           tmem_ld_wait();
           if (row < p.M) {
             float *dst = p.c + row * 256 + c0;
-            const float *tb = p.table + (int64_t)(row % p.T) * p.table_ld + 256 + c0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 tv = __ldg(reinterpret_cast<const float4 *>(tb + j));
-              *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]) + tv.x, __uint_as_float(v[j + 1]) + tv.y,
-                                                                 __uint_as_float(v[j + 2]) + tv.z, __uint_as_float(v[j + 3]) + tv.w);
-            }
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(v[4 * j]) + tv[j].x, __uint_as_float(v[4 * j + 1]) + tv[j].y,
+                                                                     __uint_as_float(v[4 * j + 2]) + tv[j].z, __uint_as_float(v[4 * j + 3]) + tv[j].w);
           }
         }
       }
@@ -303,14 +314,24 @@ __global__ void __launch_bounds__(256) k_weight_to_img(const float *__restrict__
   *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(img) + ((size_t)nt * nk + ks) * ((size_t)BN * 128) + sw128_offset(r, c)) = pk;
 }
 
+// row sums of the (T, ld) positional-encoding/bias table over columns [0,128) and [128,256)
+__global__ void k_table_sums(const float *__restrict__ table, int ld, float *__restrict__ out) {
+  const int t = blockIdx.x, part = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < 128; c += 32) s += table[(int64_t)t * ld + part * 128 + c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[t * 2 + part] = s;
+}
+
 __global__ void k_pad_bias(const float *__restrict__ b, int N, float *__restrict__ out, int Npad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Npad) out[i] = (b && i < N) ? b[i] : 0.f;
 }
 
-template <int BN, int OUT> int launch_gemm(arx_handle *h, const GemmParams &p, int n_tiles, cudaStream_t st) {
-  constexpr uint32_t smem = 2 * (A_SUB + BN * 128) + 64 + 1024;
-  auto kern = k_gemm_tc<BN, OUT>;
+template <int BN, int OUT, int NST = 2> int launch_gemm(arx_handle *h, const GemmParams &p, int n_tiles, cudaStream_t st) {
+  constexpr uint32_t smem = NST * (A_SUB + BN * 128) + (2 * NST + 1) * 8 + 16 + 1024;
+  auto kern = k_gemm_tc<BN, OUT, NST>;
   ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((p.M + 127) / 128), (unsigned)n_tiles);
   kern<<<grid, G_THREADS, smem, st>>>(p);
@@ -346,6 +367,7 @@ int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, 
   p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.M = M; p.act = act; p.c_img = c_img; p.c_nk = c_nk;
   if (L.BN == 192) return launch_gemm<192, OUT_IMG16>(h, p, L.n_tiles, st);
   if (L.BN == 256) return launch_gemm<256, OUT_IMG16>(h, p, L.n_tiles, st);
+  if (L.BN == 64) return launch_gemm<64, OUT_IMG16, 4>(h, p, L.n_tiles, st);     // deep-K layers: 4x the CTAs, 4-stage ring
   return arx_fail(h, ARX_ERR_INVALID, "tc_linear_img: unsupported BN %d", L.BN);
 }
 
@@ -371,8 +393,11 @@ int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half 
 // Fused K/V projection for T=16 pair tuples: Kq images (tuple gather + LayerNorm + scale, internal slot order)
 // and the fp32 V projections [M][256], straight from the GEMM accumulator -- no `G` round trip.
 int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
-                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, cudaStream_t st) {
+                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, float *table_sums,
+                         cudaStream_t st) {
   if (L.BN != 256 || L.n_tiles != 2) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: needs a 512-column projection");
+  k_table_sums<<<16, 64, 0, st>>>(table, table_ld, table_sums);
+  ARX_LAUNCH_CHECK(h);
   static bool slots_set = false;
   if (!slots_set) {
     ARX_CUDA(h, cudaMemcpyToSymbol(c_qslots, slots_host, 256 * sizeof(int)));
@@ -380,6 +405,6 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
   }
   GemmParams p{};
   p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;
-  p.kq_img = kq_img; p.ln_g = ln_g; p.ln_b = ln_b; p.alpha = alpha; p.table_ld = table_ld;
+  p.kq_img = kq_img; p.ln_g = ln_g; p.ln_b = ln_b; p.alpha = alpha; p.table_ld = table_ld; p.table_sums = table_sums;
   return launch_gemm<256, OUT_PROJ16>(h, p, 2, st);
 }

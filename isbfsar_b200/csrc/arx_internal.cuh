@@ -22,7 +22,8 @@ struct ArxTransformer {
   int Npad = 0;         // N rounded up to 128 (tcgen05 tile rows)
   float *pe = nullptr;      // (T,F) slice of the reference buffer
   float *wp = nullptr;      // (2cD, F): K parts then V parts of k_linear/v_linear (model.py:41-44)
-  float *bp = nullptr;      // (2cD): k bias on K part 0, v bias on V part 0, zero elsewhere
+  float *bp = nullptr;      // (T, 2cD) table: positional encoding through the projection + biases
+  float *bp_sums = nullptr; // (T, 2) row sums of the table over the two K parts
   float *ln_g = nullptr, *ln_b = nullptr;
   int32_t *tuples = nullptr; // (N,c) int32, built on device
   int32_t *q_slots = nullptr; // (128,2) internal padded-triangular order of the query tuples (T=16 pairs), -1 = pad
@@ -160,7 +161,8 @@ int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
                              float *partial, int g_ld, int g_voff, cudaStream_t st);
 
 int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
-                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, cudaStream_t st);
+                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, float *table_sums,
+                         cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);
