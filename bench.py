@@ -288,7 +288,8 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16" if path == 2 else "f32", "data": "synthetic",
                 "config": {"workload": f"cfg2: {B} query windows per GPU x 5-way 1-shot, T=16, J=30, pair tuples (N=120); "
-                                       ("step = score shard + gather scores (support set once, --static-support)" if args.static_support else "step = set/broadcast support + score shard + gather scores"),
+                                       + ("step = score shard + gather scores (support set once, --static-support)" if args.static_support
+                                          else "step = set/broadcast support + score shard + gather scores"),
                            "l2": "flushed between timed steps (256 MiB write)", "path": path,
                            "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
                 "clocks": clocks,

@@ -79,7 +79,9 @@ void free_support(arx_handle *h) {
     h->tr[i].ks_img = h->tr[i].vs_img = h->tr[i].vs_img_bf = nullptr;
   }
   cudaFree(h->ss_feat);
+  cudaFree(h->ss_poses);
   h->ss_feat = nullptr;
+  h->ss_poses = nullptr;
   h->way = h->way_cap = 0;
 }
 
@@ -270,6 +272,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     ARX_CUDA(h, cudaMemcpyAsync(flat + (size_t)c * D, w->v_b[i], D * sizeof(float), kind, st));
     rc = arx_fp32_linear(h, tr.pe, F, tr.wp, F, flat, tr.bp, 2 * c * D, h->T, 2 * c * D, F, ARX_ACT_NONE, nullptr, 1, st);
     if (rc) return rc;
+    if (c >= 2 && (rc = arx_tc_table_sums(h, tr.bp, h->T, 2 * c * D, tr.bp_sums, st))) return rc;
     // static softmax bound from the LayerNorm affine: |S| <= (max|g| sqrt(D) + ||b||_2)^2 / sqrt(D)
     std::vector<float> g(D), b(D);
     ARX_CUDA(h, cudaMemcpyAsync(g.data(), tr.ln_g, D * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -338,43 +341,39 @@ int arx_embed(arx_handle *h, const float *frames_dev, int64_t n_frames, float *f
   return ARX_OK;
 }
 
-int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way, void *stream) {
-  if (!h || !feats_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
-  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (way > h->way_cap) {
-    ARX_CUDA(h, cudaStreamSynchronize(st));
-    ARX_CUDA(h, cudaDeviceSynchronize());
-    free_support(h);
-    int rc;
-    for (int i = 0; i < h->cfg.n_transformers; ++i) {
-      if ((rc = dev_alloc(h, &h->tr[i].ks, (size_t)way * h->tr[i].N * h->D))) return rc;
-      if ((rc = dev_alloc(h, &h->tr[i].vs, (size_t)way * h->tr[i].N * h->D))) return rc;
-    }
-    if ((rc = dev_alloc(h, &h->ss_feat, (size_t)way * h->T * h->F))) return rc;
-    h->way_cap = way;
-  }
-  ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, feats_dev, (size_t)way * h->T * h->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+static int support_alloc(arx_handle *h, int way, cudaStream_t st) {
+  if (way <= h->way_cap) return ARX_OK;
+  ARX_CUDA(h, cudaStreamSynchronize(st));
+  ARX_CUDA(h, cudaDeviceSynchronize());
+  free_support(h);
+  int rc;
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
-    ArxTransformer &tr = h->tr[i];
-    size_t gbytes = (size_t)way * h->T * 2 * tr.c * h->D * sizeof(float) + 256;
-    int rc = arx_ws_reserve(h, gbytes);
-    if (rc) return rc;
-    float *G = static_cast<float *>(h->ws);
-    if ((rc = project_frames(h, tr, h->ss_feat, (int64_t)way * h->T, G, st))) return rc;
-    if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
-    if (h->cfg.force_path != 1 && arx_tc_supported(h, tr) && (rc = arx_tc_prep_support(h, tr, way, st))) return rc;
+    if ((rc = dev_alloc(h, &h->tr[i].ks, (size_t)way * h->tr[i].N * h->D))) return rc;
+    if ((rc = dev_alloc(h, &h->tr[i].vs, (size_t)way * h->tr[i].N * h->D))) return rc;
   }
-  h->way = way;
+  if ((rc = dev_alloc(h, &h->ss_feat, (size_t)way * h->T * h->F))) return rc;
+  if ((rc = dev_alloc(h, &h->ss_poses, (size_t)way * h->T * h->J3))) return rc;
+  h->way_cap = way;
   return ARX_OK;
 }
 
-int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, void *stream) {
-  if (!h || !poses_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
-  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // features go through a handle-owned scratch buffer (grown rarely), then the common path
-  const size_t need = (size_t)way * h->T * h->F * sizeof(float);
+// scratch of the support path: [x_img | h_img | f_img | G], sized for way*T rows (padded to 128)
+struct SupportScratch { __half *x_img, *h_img, *f_img; float *G; size_t bytes; };
+static SupportScratch support_scratch(arx_handle *h, int way, void *base) {
+  Carver c(base);
+  SupportScratch s{};
+  const int64_t rows_pad = ((int64_t)way * h->T + 127) / 128 * 128;
+  int maxc = 1;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) maxc = std::max(maxc, h->tr[i].c);
+  s.x_img = c.take<__half>(rows_pad * 128);
+  s.h_img = c.take<__half>(rows_pad * 192);
+  s.f_img = c.take<__half>(rows_pad * 256);
+  s.G = c.take<float>(rows_pad * 2 * maxc * h->D);
+  s.bytes = c.off + 256;
+  return s;
+}
+static int support_scratch_reserve(arx_handle *h, int way, SupportScratch *out) {
+  const size_t need = support_scratch(h, way, nullptr).bytes;
   if (need > h->ss_scratch_bytes) {
     ARX_CUDA(h, cudaDeviceSynchronize());
     cudaFree(h->ss_scratch);
@@ -383,14 +382,86 @@ int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, vo
     ARX_CUDA(h, cudaMalloc(&h->ss_scratch, need));
     h->ss_scratch_bytes = need;
   }
-  int rc = arx_embed(h, poses_dev, (int64_t)way * h->T, static_cast<float *>(h->ss_scratch), st);
-  if (rc == ARX_OK) rc = arx_set_support_features(h, static_cast<float *>(h->ss_scratch), way, st);
+  *out = support_scratch(h, way, h->ss_scratch);
+  return ARX_OK;
+}
+
+// projection + tuple/LayerNorm/image build of the support set from frame features given as an fp16 image
+// (tensor-core path) or as fp32 rows (general path)
+static int support_from_features(arx_handle *h, const __half *f_img, const float *feats32, int way, float *G, cudaStream_t st) {
+  int rc;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) {
+    ArxTransformer &tr = h->tr[i];
+    const int64_t rows = (int64_t)way * h->T;
+    if (f_img) {
+      if ((rc = arx_tc_linear_f32(h, tr.tl_proj, f_img, rows, G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
+    } else {
+      if ((rc = project_frames(h, tr, feats32, rows, G, st))) return rc;
+    }
+    const bool imgs = h->cfg.force_path != 1 && arx_tc_supported(h, tr);
+    if (h->D == 128) {
+      if ((rc = arx_tc_support_build(h, tr, G, way, imgs, st))) return rc;      // tuples + LayerNorm + operand images, one launch
+    } else {
+      if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
+    }
+  }
+  h->way = way;
+  return ARX_OK;
+}
+
+int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way, void *stream) {
+  if (!h || !feats_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = support_alloc(h, way, st))) return rc;
+  SupportScratch sc;
+  if ((rc = support_scratch_reserve(h, way, &sc))) return rc;
+  if (feats_dev != h->ss_feat)
+    ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, feats_dev, (size_t)way * h->T * h->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->ss_feat_valid = true;
+  if (h->tc_linears) {
+    if ((rc = arx_tc_rows_to_img(h, feats_dev, h->F, h->F, (int64_t)way * h->T, sc.f_img, h->tr[0].tl_proj.nk, st))) return rc;
+    return support_from_features(h, sc.f_img, nullptr, way, sc.G, st);
+  }
+  return support_from_features(h, nullptr, h->ss_feat, way, sc.G, st);
+}
+
+int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, void *stream) {
+  if (!h || !poses_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "set_support: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "set_support: weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = support_alloc(h, way, st))) return rc;
+  SupportScratch sc;
+  if ((rc = support_scratch_reserve(h, way, &sc))) return rc;
+  const int64_t rows = (int64_t)way * h->T;
+  if (h->tc_linears) {
+    // same tensor-core pipeline as the query frames; the fp32 'support_features' are derived lazily on request
+    ARX_CUDA(h, cudaMemcpyAsync(h->ss_poses, poses_dev, (size_t)rows * h->J3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    h->ss_feat_valid = false;
+    if ((rc = arx_tc_rows_to_img(h, poses_dev, h->J3, h->J3, rows, sc.x_img, h->tl_fc1.nk, st))) return rc;
+    if ((rc = arx_tc_linear_img(h, h->tl_fc1, sc.x_img, rows, ARX_ACT_RELU, sc.h_img, h->tl_fc2.nk, st))) return rc;
+    if ((rc = arx_tc_linear_img(h, h->tl_fc2, sc.h_img, rows, ARX_ACT_RELU, sc.f_img, h->tr[0].tl_proj.nk, st))) return rc;
+    return support_from_features(h, sc.f_img, nullptr, way, sc.G, st);
+  }
+  if ((rc = arx_embed(h, poses_dev, rows, h->ss_feat, st))) return rc;
+  h->ss_feat_valid = true;
+  return support_from_features(h, nullptr, h->ss_feat, way, sc.G, st);
+}
+
+static int support_features_materialise(arx_handle *h, cudaStream_t st) {
+  if (h->ss_feat_valid) return ARX_OK;
+  int rc = arx_embed(h, h->ss_poses, (int64_t)h->way * h->T, h->ss_feat, st);      // fp32 MLP (model.py:175-180)
+  if (rc == ARX_OK) h->ss_feat_valid = true;
   return rc;
 }
 
 int arx_get_support_features(arx_handle *h, float *feats_dev, void *stream) {
   if (!h || !feats_dev) return arx_fail(h, ARX_ERR_INVALID, "get_support_features: bad argument");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "get_support_features: no support set");
+  int rcm = support_features_materialise(h, static_cast<cudaStream_t>(stream));
+  if (rcm) return rcm;
   ARX_CUDA(h, cudaMemcpyAsync(feats_dev, h->ss_feat, (size_t)h->way * h->T * h->F * sizeof(float), cudaMemcpyDeviceToDevice,
                               static_cast<cudaStream_t>(stream)));
   return ARX_OK;
@@ -409,6 +480,8 @@ int arx_export_support(arx_handle *h, void *blob_dev, void *stream) {
   if (!h || !blob_dev) return arx_fail(h, ARX_ERR_INVALID, "export_support: bad argument");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "export_support: no support set");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rcm = support_features_materialise(h, st);
+  if (rcm) return rcm;
   float *p = static_cast<float *>(blob_dev);
   size_t n = (size_t)h->way * h->T * h->F;
   ARX_CUDA(h, cudaMemcpyAsync(p, h->ss_feat, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -427,17 +500,11 @@ int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *s
   if (!h || !blob_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "import_support: bad argument");
   if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "import_support: weights not loaded");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (way > h->way_cap) {
-    ARX_CUDA(h, cudaDeviceSynchronize());
-    free_support(h);
-    int rc;
-    for (int i = 0; i < h->cfg.n_transformers; ++i) {
-      if ((rc = dev_alloc(h, &h->tr[i].ks, (size_t)way * h->tr[i].N * h->D))) return rc;
-      if ((rc = dev_alloc(h, &h->tr[i].vs, (size_t)way * h->tr[i].N * h->D))) return rc;
-    }
-    if ((rc = dev_alloc(h, &h->ss_feat, (size_t)way * h->T * h->F))) return rc;
-    h->way_cap = way;
+  {
+    int rca = support_alloc(h, way, st);
+    if (rca) return rca;
   }
+  h->ss_feat_valid = true;
   const float *p = static_cast<const float *>(blob_dev);
   size_t n = (size_t)way * h->T * h->F;
   ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -396,8 +396,7 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
                          const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, float *table_sums,
                          cudaStream_t st) {
   if (L.BN != 256 || L.n_tiles != 2) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: needs a 512-column projection");
-  k_table_sums<<<16, 64, 0, st>>>(table, table_ld, table_sums);
-  ARX_LAUNCH_CHECK(h);
+  (void)table_sums;
   static bool slots_set = false;
   if (!slots_set) {
     ARX_CUDA(h, cudaMemcpyToSymbol(c_qslots, slots_host, 256 * sizeof(int)));
@@ -407,4 +406,10 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
   p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;
   p.kq_img = kq_img; p.ln_g = ln_g; p.ln_b = ln_b; p.alpha = alpha; p.table_ld = table_ld; p.table_sums = table_sums;
   return launch_gemm<256, OUT_PROJ16>(h, p, 2, st);
+}
+
+int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *out, cudaStream_t st) {
+  k_table_sums<<<T, 64, 0, st>>>(table, ld, out);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
 }

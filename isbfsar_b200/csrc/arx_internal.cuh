@@ -57,6 +57,8 @@ struct arx_handle {
   float *ss_feat = nullptr;   // (W,T,F)
   void *ss_scratch = nullptr;
   size_t ss_scratch_bytes = 0;
+  float *ss_poses = nullptr;       // copy of the support poses when the features were produced on tensor cores
+  bool ss_feat_valid = false;      // ss_feat holds fp32 features (else they are derived lazily from ss_poses)
   // workspace (grown on demand)
   void *ws = nullptr;
   size_t ws_bytes = 0;
@@ -118,6 +120,7 @@ int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float 
 // ---- tcgen05 kernels (arx_tc.cu) -------------------------------------------------
 bool arx_tc_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
+int arx_tc_support_build(arx_handle *h, ArxTransformer &tr, const float *G, int way, bool with_images, cudaStream_t st);
 int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st);
 bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
@@ -163,6 +166,8 @@ int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
 int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
                          const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, float *table_sums,
                          cudaStream_t st);
+
+int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *out, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

@@ -466,6 +466,62 @@ __global__ void __launch_bounds__(256) k_prep_kc_img(const float *__restrict__ k
   }
 }
 
+// Support side in ONE launch (model.py:69-84 for the support set): tuple gather, LayerNorm, fp32 K/V tuple tensors
+// (general path, export blob) and the three tcgen05 operand images (Kc fp16, Vc^T fp16 and bf16).  One block per class.
+__global__ void __launch_bounds__(256) k_support_build(const float *__restrict__ G, const int32_t *__restrict__ tuples,
+                                                       const float *__restrict__ ln_g, const float *__restrict__ ln_b,
+                                                       float *__restrict__ ks, float *__restrict__ vs, __half *__restrict__ kc_img,
+                                                       __half *__restrict__ vct_img, __half *__restrict__ vct_img_bf, int T, int c, int N,
+                                                       int ldg) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t cls = blockIdx.x;
+  const int d0 = lane * 4;
+  const float4 g = *reinterpret_cast<const float4 *>(ln_g + d0);
+  const float4 be = *reinterpret_cast<const float4 *>(ln_b + d0);
+  uint8_t *kc = kc_img ? reinterpret_cast<uint8_t *>(kc_img) + cls * IMG_BYTES : nullptr;
+  uint8_t *vt = vct_img ? reinterpret_cast<uint8_t *>(vct_img) + cls * IMG_BYTES : nullptr;
+  uint8_t *vb = vct_img_bf ? reinterpret_cast<uint8_t *>(vct_img_bf) + cls * IMG_BYTES : nullptr;
+  const int rows = kc ? TILE : N;
+  for (int r = blockIdx.y * 8 + warp; r < rows; r += 8 * gridDim.y) {
+    float4 k = make_float4(0, 0, 0, 0), v = make_float4(0, 0, 0, 0);
+    uint2 kpk = make_uint2(0u, 0u);
+    if (r < N) {
+      for (int pp = 0; pp < c; ++pp) {
+        const int fr = tuples[r * c + pp];
+        const float *row = G + (cls * T + fr) * (size_t)ldg;
+        const float4 a = *reinterpret_cast<const float4 *>(row + pp * DD + d0);
+        const float4 b = *reinterpret_cast<const float4 *>(row + (c + pp) * DD + d0);
+        k.x += a.x; k.y += a.y; k.z += a.z; k.w += a.w;
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      }
+      float sum = k.x + k.y + k.z + k.w;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / DD;
+      const float4 dl = make_float4(k.x - mean, k.y - mean, k.z - mean, k.w - mean);
+      float q = dl.x * dl.x + dl.y * dl.y + dl.z * dl.z + dl.w * dl.w;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = 1.0f / sqrtf(q / DD + 1e-5f);
+      k = make_float4(dl.x * rstd * g.x + be.x, dl.y * rstd * g.y + be.y, dl.z * rstd * g.z + be.z, dl.w * rstd * g.w + be.w);
+      *reinterpret_cast<float4 *>(ks + (cls * N + r) * DD + d0) = k;
+      *reinterpret_cast<float4 *>(vs + (cls * N + r) * DD + d0) = v;
+      kpk.x = pack_half2(k.x, k.y);
+      kpk.y = pack_half2(k.z, k.w);
+    }
+    if (kc) {
+      *reinterpret_cast<uint2 *>(kc + (d0 >> 6) * SUB_BYTES + sw128_offset(r, d0 & 63)) = kpk;      // row r (zero beyond N)
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {                                                                 // column r of Vc^T (zero beyond N)
+        const uint32_t off = (r >> 6) * SUB_BYTES + sw128_offset(d0 + e, r & 63);
+        *reinterpret_cast<__half *>(vt + off) = __float2half_rn(vv[e]);
+        *reinterpret_cast<__nv_bfloat16 *>(vb + off) = __float2bfloat16_rn(vv[e]);
+      }
+    }
+  }
+}
+
 __global__ void k_finish_tc(const float *__restrict__ partial, float *__restrict__ logits, int32_t *__restrict__ chosen, int64_t n_win,
                             int way, int N) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -915,6 +971,20 @@ int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
   ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H_SMEM_BYTES));
   kern<<<grid, NTHREADS, H_SMEM_BYTES, st>>>(p);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
+}
+
+// One-launch support build from the per-frame projections G (way*T, 2cD); with_images also fills the tcgen05 operands.
+int arx_tc_support_build(arx_handle *h, ArxTransformer &tr, const float *G, int way, bool with_images, cudaStream_t st) {
+  if (with_images && !tr.ks_img) {
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.ks_img), (size_t)h->way_cap * IMG_BYTES));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.vs_img), (size_t)h->way_cap * IMG_BYTES));
+  }
+  if (with_images && !tr.vs_img_bf) ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.vs_img_bf), (size_t)h->way_cap * IMG_BYTES));
+  k_support_build<<<dim3(way, 8), 256, 0, st>>>(G, tr.tuples, tr.ln_g, tr.ln_b, tr.ks, tr.vs, with_images ? tr.ks_img : nullptr,
+                                       with_images ? tr.vs_img : nullptr, with_images ? tr.vs_img_bf : nullptr, h->T, tr.c, tr.N,
+                                       2 * tr.c * h->D);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }

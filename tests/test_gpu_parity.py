@@ -111,7 +111,9 @@ def test_forward_reference_api():
     # cached path: ss_features expanded over the batch (ar.py:56-61 / SURVEY 3.3)
     ssf = out["support_features"][:1]
     out2 = m(None, torch.from_numpy(labels).cuda(), {"sk": Q}, ss_features=ssf.expand(8, -1, -1, -1))
-    assert rel_err(out2["logits"].cpu(), out["logits"].cpu()).max() < 1e-5
+    # (features given in fp32 enter the fp16 pipeline one stage later than poses do: equal within the tolerance)
+    assert rel_err(out2["logits"].cpu(), out["logits"].cpu()).max() < tol
+    assert rel_err(out2["logits"].cpu(), ref["logits"]).max() < tol
     # label permutation: logits column k belongs to class ss_labels[0][k]
     perm = np.array([[3, 1, 4, 0, 2]], dtype=np.int32)
     out3 = m({"sk": S}, torch.from_numpy(perm).cuda(), {"sk": Q})
