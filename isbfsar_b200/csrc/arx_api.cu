@@ -74,9 +74,9 @@ int upload(arx_handle *h, float *dst, const float *src, size_t n, bool on_device
 void free_support(arx_handle *h) {
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
     cudaFree(h->tr[i].ks); cudaFree(h->tr[i].vs);
-    cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img); cudaFree(h->tr[i].vs_img_bf);
+    cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img); cudaFree(h->tr[i].vs_img_bf); cudaFree(h->tr[i].uc_img);
     h->tr[i].ks = h->tr[i].vs = nullptr;
-    h->tr[i].ks_img = h->tr[i].vs_img = h->tr[i].vs_img_bf = nullptr;
+    h->tr[i].ks_img = h->tr[i].vs_img = h->tr[i].vs_img_bf = h->tr[i].uc_img = nullptr;
   }
   cudaFree(h->ss_feat);
   cudaFree(h->ss_poses);
@@ -89,6 +89,7 @@ void free_support(arx_handle *h) {
 struct Fp32Ws {
   float *H1, *FE, *G, *Kq, *Vq, *Z, *partial, *y, *h1, *h2;
   __half *kq_img, *x_img, *h_img, *f_img, *y_img, *h1_img;
+  float *uab;
   size_t bytes;
 };
 Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, void *base,
@@ -103,6 +104,7 @@ Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, b
   w.f_img = tcl ? c.take<__half>(rows_pad * 256) : nullptr;
   w.y_img = (tcl && tc_head && disc) ? c.take<__half>(n_pad * (int64_t)h->tl_d1.nk * 64) : nullptr;
   w.h1_img = (tcl && tc_head && disc) ? c.take<__half>(n_pad * 256) : nullptr;
+  w.uab = (tcl && tc_head && disc) ? c.take<float>(rows_pad * 32) : nullptr;
   w.H1 = (from_frames && !tcl) ? c.take<float>(n * h->T * h->H) : nullptr;
   w.FE = (from_frames && !tcl) ? c.take<float>(n * h->T * h->F) : nullptr;
   w.G = c.take<float>(n * h->T * 2 * tr.c * h->D);
@@ -226,7 +228,14 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
   cudaFree(h->wdr_img);
   for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2}) { cudaFree(L->w_img); cudaFree(L->bias); }
-  for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) { cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); }
+  for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
+    cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); cudaFree(h->tr[i].tl_uab.w_img); cudaFree(h->tr[i].tl_uab.bias);
+    cudaFree(h->tr[i].wc); cudaFree(h->tr[i].tcomp);
+  }
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_support_done) cudaEventDestroy(h->ev_support_done);
+  if (h->ev_score_done) cudaEventDestroy(h->ev_score_done);
   cudaFree(h->ws);
   cudaFree(h->ss_scratch);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
@@ -305,6 +314,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
       const int K1 = h->T * (h->T - 1) / 2 * h->T;
       if ((rc = arx_tc_linear_prepare(h, h->tl_d1, h->d1_w, K1, h->d1_b, 256, K1, 64, st))) return rc;
       if ((rc = arx_tc_linear_prepare(h, h->tl_d2, h->d2_w, 256, h->d2_b, 64, 256, 64, st))) return rc;
+      if (h->T == 16 && h->tr[0].c == 2 && (rc = arx_tc2_head_prepare_weights(h, h->tr[0], st))) return rc;
     }
     h->tc_linears = true;
   }
@@ -338,6 +348,32 @@ int arx_embed(arx_handle *h, const float *frames_dev, int64_t n_frames, float *f
     rc = embed_frames(h, frames_dev + r0 * h->J3, r, static_cast<float *>(h->ws), feats_dev + r0 * h->F, st);
     if (rc) return rc;
   }
+  return ARX_OK;
+}
+
+// fork the support chain onto the side stream (after everything already queued on the caller's stream and after
+// the last scoring pass that still reads the current operands)
+static int support_fork(arx_handle *h, cudaStream_t st, cudaStream_t *side) {
+  if (!h->side_stream) {
+    ARX_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_support_done, cudaEventDisableTiming));
+    ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
+  }
+  ARX_CUDA(h, cudaEventRecord(h->ev_fork, st));
+  ARX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+  if (h->score_recorded) ARX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_score_done, 0));
+  *side = h->side_stream;
+  return ARX_OK;
+}
+static int support_join_record(arx_handle *h) {
+  ARX_CUDA(h, cudaEventRecord(h->ev_support_done, h->side_stream));
+  h->support_recorded = true;
+  return ARX_OK;
+}
+// consumers of the support operands on stream st
+static int support_wait(arx_handle *h, cudaStream_t st) {
+  if (h->support_recorded) ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_support_done, 0));
   return ARX_OK;
 }
 
@@ -401,6 +437,7 @@ static int support_from_features(arx_handle *h, const __half *f_img, const float
     const bool imgs = h->cfg.force_path != 1 && arx_tc_supported(h, tr);
     if (h->D == 128) {
       if ((rc = arx_tc_support_build(h, tr, G, way, imgs, st))) return rc;      // tuples + LayerNorm + operand images, one launch
+      if (imgs && i == 0 && h->tc_linears && h->cfg.has_discriminator && h->T == 16 && tr.c == 2 && (rc = arx_tc2_support_uc(h, tr, way, st))) return rc;
     } else {
       if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
     }
@@ -417,14 +454,20 @@ int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way,
   if ((rc = support_alloc(h, way, st))) return rc;
   SupportScratch sc;
   if ((rc = support_scratch_reserve(h, way, &sc))) return rc;
+  if ((rc = support_wait(h, st))) return rc;                       // a previous chain may still be writing ss_feat
   if (feats_dev != h->ss_feat)
     ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, feats_dev, (size_t)way * h->T * h->F * sizeof(float), cudaMemcpyDeviceToDevice, st));
   h->ss_feat_valid = true;
+  cudaStream_t ss;
+  if ((rc = support_fork(h, st, &ss))) return rc;                  // the caller's buffer is not touched past this point
   if (h->tc_linears) {
-    if ((rc = arx_tc_rows_to_img(h, feats_dev, h->F, h->F, (int64_t)way * h->T, sc.f_img, h->tr[0].tl_proj.nk, st))) return rc;
-    return support_from_features(h, sc.f_img, nullptr, way, sc.G, st);
+    if ((rc = arx_tc_rows_to_img(h, h->ss_feat, h->F, h->F, (int64_t)way * h->T, sc.f_img, h->tr[0].tl_proj.nk, ss))) return rc;
+    rc = support_from_features(h, sc.f_img, nullptr, way, sc.G, ss);
+  } else {
+    rc = support_from_features(h, nullptr, h->ss_feat, way, sc.G, ss);
   }
-  return support_from_features(h, nullptr, h->ss_feat, way, sc.G, st);
+  if (rc) return rc;
+  return support_join_record(h);
 }
 
 int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, void *stream) {
@@ -436,21 +479,31 @@ int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, vo
   SupportScratch sc;
   if ((rc = support_scratch_reserve(h, way, &sc))) return rc;
   const int64_t rows = (int64_t)way * h->T;
+  if ((rc = support_wait(h, st))) return rc;                       // a previous chain may still be reading ss_poses
+  ARX_CUDA(h, cudaMemcpyAsync(h->ss_poses, poses_dev, (size_t)rows * h->J3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  cudaStream_t ss;
+  if ((rc = support_fork(h, st, &ss))) return rc;                  // the caller's buffer is not touched past this point
   if (h->tc_linears) {
     // same tensor-core pipeline as the query frames; the fp32 'support_features' are derived lazily on request
-    ARX_CUDA(h, cudaMemcpyAsync(h->ss_poses, poses_dev, (size_t)rows * h->J3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     h->ss_feat_valid = false;
-    if ((rc = arx_tc_rows_to_img(h, poses_dev, h->J3, h->J3, rows, sc.x_img, h->tl_fc1.nk, st))) return rc;
-    if ((rc = arx_tc_linear_img(h, h->tl_fc1, sc.x_img, rows, ARX_ACT_RELU, sc.h_img, h->tl_fc2.nk, st))) return rc;
-    if ((rc = arx_tc_linear_img(h, h->tl_fc2, sc.h_img, rows, ARX_ACT_RELU, sc.f_img, h->tr[0].tl_proj.nk, st))) return rc;
-    return support_from_features(h, sc.f_img, nullptr, way, sc.G, st);
+    if ((rc = arx_tc_rows_to_img(h, h->ss_poses, h->J3, h->J3, rows, sc.x_img, h->tl_fc1.nk, ss))) return rc;
+    if ((rc = arx_tc_linear_img(h, h->tl_fc1, sc.x_img, rows, ARX_ACT_RELU, sc.h_img, h->tl_fc2.nk, ss))) return rc;
+    if ((rc = arx_tc_linear_img(h, h->tl_fc2, sc.h_img, rows, ARX_ACT_RELU, sc.f_img, h->tr[0].tl_proj.nk, ss))) return rc;
+    rc = support_from_features(h, sc.f_img, nullptr, way, sc.G, ss);
+  } else {
+    // general path: arx_embed stages through the shared workspace, so it stays on the caller's stream
+    if ((rc = arx_embed(h, h->ss_poses, rows, h->ss_feat, st))) return rc;
+    h->ss_feat_valid = true;
+    if ((rc = support_fork(h, st, &ss))) return rc;
+    rc = support_from_features(h, nullptr, h->ss_feat, way, sc.G, ss);
   }
-  if ((rc = arx_embed(h, poses_dev, rows, h->ss_feat, st))) return rc;
-  h->ss_feat_valid = true;
-  return support_from_features(h, nullptr, h->ss_feat, way, sc.G, st);
+  if (rc) return rc;
+  return support_join_record(h);
 }
 
 static int support_features_materialise(arx_handle *h, cudaStream_t st) {
+  int rcw = support_wait(h, st);
+  if (rcw) return rcw;
   if (h->ss_feat_valid) return ARX_OK;
   int rc = arx_embed(h, h->ss_poses, (int64_t)h->way * h->T, h->ss_feat, st);      // fp32 MLP (model.py:175-180)
   if (rc == ARX_OK) h->ss_feat_valid = true;
@@ -503,6 +556,10 @@ int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *s
   {
     int rca = support_alloc(h, way, st);
     if (rca) return rca;
+  }
+  {
+    int rcw = support_wait(h, st);
+    if (rcw) return rcw;
   }
   h->ss_feat_valid = true;
   const float *p = static_cast<const float *>(blob_dev);
@@ -560,6 +617,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const bool tcl = use_tc && h->tc_linears && (h->tc_variant & 4) == 0;
   // fused projection epilogue (Kq images + compact V projections): T=16 pairs, slot order, no fp32 tuple tensors needed
   const bool fused_proj = tcl && mode0 && arx_tc_slot_order(h, tr) && !tuples32 && (h->tc_variant & 16) == 0;
+  const bool head2 = fused_proj && tc_head && ti == 0 && h->tr[0].uc_img != nullptr && (h->tc_variant & 32) == 0;   // second-generation head pass
   const int g_ld = fused_proj ? 2 * h->D : 2 * tr.c * h->D;      // row stride of G as the attention epilogues see it
   const int g_voff = fused_proj ? 0 : tr.c * h->D;
   const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32, tcl, tc_head);
@@ -592,6 +650,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
         if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G, tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
           return rc;
+        if (head2 && (rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, rows, w.uab, 32, tr.tcomp, h->T, st))) return rc;
       } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, rows, w.G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
     } else {
       if (from_frames) {
@@ -606,6 +665,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     if ((rc = prof_mark(h, 2, st))) return rc;
     if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
     if (use_tc && !fused_proj && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
+    if ((rc = support_wait(h, st))) return rc;                   // join the support chain (side stream) before its operands are read
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
@@ -614,8 +674,10 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
                                  h->tc_variant, g_ld, g_voff, st)))
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
-      if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
-                                                        h->tl_d1.nk, g_ld, g_voff, st)))
+      if (disc && head2) {
+        if ((rc = arx_tc2_head_launch(h, tr, w.kq_img, w.uab, n, ch, w.y_img, h->tl_d1.nk, st))) return rc;
+      } else if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
+                                                               h->tl_d1.nk, g_ld, g_voff, st)))
         return rc;
       if (disc && !tc_head && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
     } else {
@@ -634,6 +696,10 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
       if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
     }
     if ((rc = prof_mark(h, 5, st))) return rc;
+  }
+  if (h->ev_score_done) {
+    ARX_CUDA(h, cudaEventRecord(h->ev_score_done, st));
+    h->score_recorded = true;
   }
   return ARX_OK;
 }

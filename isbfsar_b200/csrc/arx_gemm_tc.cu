@@ -413,3 +413,13 @@ int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *o
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }
+
+// A.W^T + table[row % T] -> fp32 row-major for a narrow (32-column) layer
+int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
+                            cudaStream_t st) {
+  GemmParams p{};
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
+  p.table = table; p.T = T;
+  if (L.BN == 32) return launch_gemm<32, OUT_F32>(h, p, L.n_tiles, st);
+  return arx_fail(h, ARX_ERR_INVALID, "tc_linear_f32_small: unsupported BN %d", L.BN);
+}

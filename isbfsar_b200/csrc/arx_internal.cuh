@@ -34,6 +34,9 @@ struct ArxTransformer {
   __half *vs_img_bf = nullptr;   // Vc^T as bf16 (prototype MMA of arx_tc2.cu)
   float softmax_bound = 0.f; // static |S| bound from LayerNorm affine
   ArxTcLinear tl_proj;       // K/V projection (2cD x F) on tensor cores
+  ArxTcLinear tl_uab;        // 32 composite columns Wdr.Wv of the second-generation head pass
+  float *wc = nullptr, *tcomp = nullptr;   // composite weights (32,F) and table (T,32)
+  __half *uc_img = nullptr;  // per class Wdr.Vc^T (16 x 128 fp16 B operand)
 };
 
 struct arx_handle {
@@ -57,6 +60,11 @@ struct arx_handle {
   float *ss_feat = nullptr;   // (W,T,F)
   void *ss_scratch = nullptr;
   size_t ss_scratch_bytes = 0;
+  // the support chain runs on an internal side stream, overlapped with the query-side frame kernels of the next
+  // arx_score; consumers join on ev_support_done, producers wait for ev_score_done (operands still being read)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_support_done = nullptr, ev_score_done = nullptr;
+  bool support_recorded = false, score_recorded = false;
   float *ss_poses = nullptr;       // copy of the support poses when the features were produced on tensor cores
   bool ss_feat_valid = false;      // ss_feat holds fp32 features (else they are derived lazily from ss_poses)
   // workspace (grown on demand)
@@ -168,6 +176,13 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
                          cudaStream_t st);
 
 int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *out, cudaStream_t st);
+
+int arx_tc2_head_prepare_weights(arx_handle *h, ArxTransformer &tr, cudaStream_t st);
+int arx_tc2_support_uc(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
+int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *uab, int64_t n_win, const int32_t *chosen,
+                        __half *y_img, int y_nk, cudaStream_t st);
+int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
+                            cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);
