@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <algorithm>
 
@@ -740,8 +741,12 @@ int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, fl
   const int way = h->way;
   const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);
   const size_t out_per = (size_t)(way + 2) * sizeof(float);   // logits | is_true | chosen
-  // copy/compute overlap needs several chunks per call: stage at most 1024 windows at a time
-  const int64_t stage = std::min<int64_t>(n_windows, std::min<int64_t>(h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096, 1024));
+  // copy/compute overlap needs at least two chunks per call, but small chunks waste the GPU (fixed per-launch costs):
+  // halve the batch (rounded to whole 128-row tiles), never below 1024 windows
+  int64_t stage = h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096;
+  if (const char *e = getenv("ARX_HOST_STAGE")) stage = atoll(e);
+  else stage = std::min<int64_t>(stage, std::max<int64_t>(1024, ((n_windows + 1) / 2 + 127) / 128 * 128));
+  stage = std::max<int64_t>(1, std::min<int64_t>(stage, n_windows));
   if ((size_t)stage > h->stage_windows || way != h->stage_way) {
     // (re)allocate staging sized for `stage` windows at the current way
     ARX_CUDA(h, cudaDeviceSynchronize());
