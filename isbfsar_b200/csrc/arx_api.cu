@@ -102,7 +102,7 @@ Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, b
   const int64_t rows_pad = (n * h->T + 127) / 128 * 128, n_pad = (n + 127) / 128 * 128;
   w.x_img = (tcl && from_frames) ? c.take<__half>(rows_pad * 128) : nullptr;
   w.h_img = (tcl && from_frames) ? c.take<__half>(rows_pad * 192) : nullptr;
-  w.f_img = tcl ? c.take<__half>(rows_pad * 256) : nullptr;
+  w.f_img = tcl ? c.take<__half>(rows_pad * 320) : nullptr;      // 4 feature sub-tiles + the one-hot sub-tile
   w.y_img = (tcl && tc_head && disc) ? c.take<__half>(n_pad * (int64_t)h->tl_d1.nk * 64) : nullptr;
   w.h1_img = (tcl && tc_head && disc) ? c.take<__half>(n_pad * 256) : nullptr;
   w.uab = (tcl && tc_head && disc) ? c.take<float>(rows_pad * 32) : nullptr;
@@ -223,7 +223,7 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->fc1_w); cudaFree(h->fc1_b); cudaFree(h->fc2_w); cudaFree(h->fc2_b);
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     ArxTransformer &tr = h->tr[i];
-    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots); cudaFree(tr.bp_sums);
+    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots); cudaFree(tr.bp_sums); cudaFree(tr.wp_ext);
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
@@ -309,7 +309,13 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     if ((rc = arx_tc_linear_prepare(h, h->tl_fc2, h->fc2_w, h->H, h->fc2_b, h->F, h->H, 256, st))) return rc;
     for (int i = 0; i < h->cfg.n_transformers; ++i) {
       ArxTransformer &tr = h->tr[i];
-      if ((rc = arx_tc_linear_prepare(h, tr.tl_proj, tr.wp, h->F, nullptr, 2 * tr.c * h->D, h->F, 256, st))) return rc;
+      tr.table_in_gemm = (h->T == 16);
+      if (tr.table_in_gemm) {
+        // the positional-encoding / bias table rides through the GEMM: 32 one-hot K columns against hi/lo(table)
+        if (!tr.wp_ext) ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.wp_ext), (size_t)2 * tr.c * h->D * (h->F + 32) * sizeof(float)));
+        if ((rc = arx_tc_build_wp_ext(h, tr.wp, tr.bp, tr.wp_ext, 2 * tr.c * h->D, h->F, st))) return rc;
+        if ((rc = arx_tc_linear_prepare(h, tr.tl_proj, tr.wp_ext, h->F + 32, nullptr, 2 * tr.c * h->D, h->F + 32, 256, st))) return rc;
+      } else if ((rc = arx_tc_linear_prepare(h, tr.tl_proj, tr.wp, h->F, nullptr, 2 * tr.c * h->D, h->F, 256, st))) return rc;
     }
     if (h->cfg.has_discriminator) {
       const int K1 = h->T * (h->T - 1) / 2 * h->T;
@@ -404,7 +410,7 @@ static SupportScratch support_scratch(arx_handle *h, int way, void *base) {
   for (int i = 0; i < h->cfg.n_transformers; ++i) maxc = std::max(maxc, h->tr[i].c);
   s.x_img = c.take<__half>(rows_pad * 128);
   s.h_img = c.take<__half>(rows_pad * 192);
-  s.f_img = c.take<__half>(rows_pad * 256);
+  s.f_img = c.take<__half>(rows_pad * 320);
   s.G = c.take<float>(rows_pad * 2 * maxc * h->D);
   s.bytes = c.off + 256;
   return s;
@@ -431,7 +437,8 @@ static int support_from_features(arx_handle *h, const __half *f_img, const float
     ArxTransformer &tr = h->tr[i];
     const int64_t rows = (int64_t)way * h->T;
     if (f_img) {
-      if ((rc = arx_tc_linear_f32(h, tr.tl_proj, f_img, rows, G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
+      if ((rc = arx_tc_linear_f32(h, tr.tl_proj, f_img, h->tr[0].tl_proj.nk, rows, G, 2 * tr.c * h->D, tr.table_in_gemm ? nullptr : tr.bp, h->T, st)))
+        return rc;
     } else {
       if ((rc = project_frames(h, tr, feats32, rows, G, st))) return rc;
     }
@@ -462,7 +469,9 @@ int arx_set_support_features(arx_handle *h, const float *feats_dev, int32_t way,
   cudaStream_t ss;
   if ((rc = support_fork(h, st, &ss))) return rc;                  // the caller's buffer is not touched past this point
   if (h->tc_linears) {
-    if ((rc = arx_tc_rows_to_img(h, h->ss_feat, h->F, h->F, (int64_t)way * h->T, sc.f_img, h->tr[0].tl_proj.nk, ss))) return rc;
+    if ((rc = arx_tc_rows_to_img(h, h->ss_feat, h->F, h->F, (int64_t)way * h->T, sc.f_img, h->tr[0].tl_proj.nk,
+                                 h->tr[0].table_in_gemm ? h->tr[0].tl_proj.nk - 1 : -1, ss)))
+      return rc;
     rc = support_from_features(h, sc.f_img, nullptr, way, sc.G, ss);
   } else {
     rc = support_from_features(h, nullptr, h->ss_feat, way, sc.G, ss);
@@ -487,9 +496,11 @@ int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, vo
   if (h->tc_linears) {
     // same tensor-core pipeline as the query frames; the fp32 'support_features' are derived lazily on request
     h->ss_feat_valid = false;
-    if ((rc = arx_tc_rows_to_img(h, h->ss_poses, h->J3, h->J3, rows, sc.x_img, h->tl_fc1.nk, ss))) return rc;
-    if ((rc = arx_tc_linear_img(h, h->tl_fc1, sc.x_img, rows, ARX_ACT_RELU, sc.h_img, h->tl_fc2.nk, ss))) return rc;
-    if ((rc = arx_tc_linear_img(h, h->tl_fc2, sc.h_img, rows, ARX_ACT_RELU, sc.f_img, h->tr[0].tl_proj.nk, ss))) return rc;
+    if ((rc = arx_tc_rows_to_img(h, h->ss_poses, h->J3, h->J3, rows, sc.x_img, h->tl_fc1.nk, -1, ss))) return rc;
+    if ((rc = arx_tc_linear_img(h, h->tl_fc1, sc.x_img, rows, ARX_ACT_RELU, sc.h_img, h->tl_fc2.nk, -1, ss))) return rc;
+    if ((rc = arx_tc_linear_img(h, h->tl_fc2, sc.h_img, rows, ARX_ACT_RELU, sc.f_img, h->tr[0].tl_proj.nk,
+                                h->tr[0].table_in_gemm ? h->tr[0].tl_proj.nk - 1 : -1, ss)))
+      return rc;
     rc = support_from_features(h, sc.f_img, nullptr, way, sc.G, ss);
   } else {
     // general path: arx_embed stages through the shared workspace, so it stays on the caller's stream
@@ -634,25 +645,28 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     const float *FE;
     if ((rc = prof_mark(h, 0, st))) return rc;
     const int64_t rows = n * h->T;
+    const int f_nk = tr.tl_proj.nk, f_onehot = tr.table_in_gemm ? f_nk - 1 : -1;     // feature image: + one-hot sub-tile
     if (tcl) {
       // frame MLP + projection on tensor cores, activations chained as fp16 images
       FE = nullptr;
       if (from_frames) {
-        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, st))) return rc;
-        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, st))) return rc;
-        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, tr.tl_proj.nk, st))) return rc;
+        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
       } else {
-        if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, tr.tl_proj.nk, st))) return rc;
+        if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, f_nk, f_onehot, st))) return rc;
       }
       if ((rc = prof_mark(h, 1, st))) return rc;
       if (fused_proj) {
         int32_t slots[256];
         arx_tc2_slot_table(slots);
-        const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
-        if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G, tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
+        const float alpha = (h->tc_variant & 64) ? -1.f : ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);   // bit 6: timing-only, skip the tuple build
+        if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G,
+                                       tr.table_in_gemm ? nullptr : tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
           return rc;
-        if (head2 && (rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, rows, w.uab, 32, tr.tcomp, h->T, st))) return rc;
-      } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, rows, w.G, 2 * tr.c * h->D, tr.bp, h->T, st))) return rc;
+        if (head2 && (rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows, w.uab, 32, tr.tcomp, h->T, st))) return rc;
+      } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, 2 * tr.c * h->D, tr.table_in_gemm ? nullptr : tr.bp, h->T, st)))
+        return rc;
     } else {
       if (from_frames) {
         if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, rows, w.H1, w.FE, st))) return rc;
@@ -688,7 +702,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
       if ((rc = prof_mark(h, 4, st))) return rc;
     }
     if (disc && w.y_img) {
-      if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, st))) return rc;
+      if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
       if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true_dev + b0, st))) return rc;
     } else if (disc) {
       const int K1 = tr.N * h->T;

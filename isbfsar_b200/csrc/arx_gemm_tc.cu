@@ -25,7 +25,9 @@ struct GemmParams {
   const __half *a_img;     // [m_tiles][nk][128 x 64]
   const __half *w_img;     // [n_tiles][nk][BN x 64]
   const float *bias;       // [n_tiles*BN] (zero padded) or null
-  int nk;                  // K sub-tiles of 64
+  int nk;                  // K sub-tiles of 64 consumed by this GEMM
+  int a_nk;                // sub-tiles per row tile of the A image (>= nk)
+  int onehot_sub;          // OUT_IMG16: also write a one-hot(row % 16) sub-tile at this index of c_img (-1 = no)
   int64_t M;               // valid rows
   int act;                 // ARX_ACT_*
   // OUT_IMG16
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 
   if (warp == 4) {
     if (elect_one()) {
-      const uint8_t *a = reinterpret_cast<const uint8_t *>(p.a_img) + (size_t)mt * p.nk * A_SUB;
+      const uint8_t *a = reinterpret_cast<const uint8_t *>(p.a_img) + (size_t)mt * p.a_nk * A_SUB;
       const uint8_t *w = reinterpret_cast<const uint8_t *>(p.w_img) + (size_t)nt * p.nk * B_SUB;
       for (int ks = 0; ks < p.nk; ++ks) {
         const int st = ks % NST;
@@ -119,8 +121,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
         be.x *= p.alpha; be.y *= p.alpha; be.z *= p.alpha; be.w *= p.alpha;
         // LayerNorm mean by linearity: mean(A_i + B_j) = mean(A_i) + mean(B_j), and every lane holds one whole frame
         // row in its registers while staging -- so the rows are stored CENTRED and a tuple needs one reduction only.
-        const float *tb = p.table + (int64_t)(lane & 15) * p.table_ld;
-        float sumA = __ldg(p.table_sums + (lane & 15) * 2), sumB = __ldg(p.table_sums + (lane & 15) * 2 + 1);   // row sums of the table
+        const bool has_tb = p.table != nullptr;      // null: the table came in through the one-hot K columns
+        const float *tb = has_tb ? p.table + (int64_t)(lane & 15) * p.table_ld : nullptr;
+        float sumA = has_tb ? __ldg(p.table_sums + (lane & 15) * 2) : 0.f, sumB = has_tb ? __ldg(p.table_sums + (lane & 15) * 2 + 1) : 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t v[32];
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
             tmem_ld32(tmem + lane_base + c0, v);
             float4 tv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tv[j] = __ldg(reinterpret_cast<const float4 *>(tb + c0) + j);     // in flight with the TMEM load
+            for (int j = 0; j < 8; ++j) tv[j] = has_tb ? __ldg(reinterpret_cast<const float4 *>(tb + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
             if ((lane >> 4) == wi) {
               const float m = c0 < 128 ? mA : mB;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
             }
           }
           __syncwarp();
-          if (win * 16 < p.M) {
+          if (win * 16 < p.M && p.alpha > 0.f) {
             uint8_t *out = reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768;
             // NU tuple rows per iteration so that their variance reductions (5 dependent shuffles each) interleave
             constexpr int NU = 8;
@@ -197,10 +200,11 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_base + c0, v);
-          const float *tb = p.table + (int64_t)(row % p.T) * p.table_ld + 256 + c0;
           float4 tv[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) tv[j] = __ldg(reinterpret_cast<const float4 *>(tb) + j);
+          for (int j = 0; j < 8; ++j)
+            tv[j] = p.table ? __ldg(reinterpret_cast<const float4 *>(p.table + (int64_t)(row % p.T) * p.table_ld + 256 + c0) + j)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
           tmem_ld_wait();
           if (row < p.M) {
             float *dst = p.c + row * 256 + c0;
@@ -212,6 +216,24 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
         }
       }
     } else {
+    if constexpr (OUT == OUT_IMG16) {
+      if (p.onehot_sub >= 0 && nt == 0) {
+        // extra K columns for the next GEMM: one-hot(frame position) twice (against the hi and lo halves of the
+        // positional-encoding / bias table), so that the table is added by the tensor core (model.py:27,75-78)
+        uint8_t *dst = reinterpret_cast<uint8_t *>(p.c_img) + ((size_t)mt * p.c_nk + p.onehot_sub) * A_SUB;
+        const int t = r & 15;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+          if (ch == (t >> 3) || ch == 2 + (t >> 3)) {
+            const uint32_t one = 0x3C00u << (16 * (t & 1));         // fp16 1.0 in the low or high half
+            const int w = (t & 7) >> 1;
+            pk.x = w == 0 ? one : 0u; pk.y = w == 1 ? one : 0u; pk.z = w == 2 ? one : 0u; pk.w = w == 3 ? one : 0u;
+          }
+          *reinterpret_cast<uint4 *>(dst + sw128_offset(r, ch * 8)) = pk;
+        }
+      }
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -269,7 +291,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 }
 
 // fp32 row-major [M][lda] (K valid columns) -> fp16 activation image [ceil(M/128)][nk][128 x 64]; zero padded.
-__global__ void __launch_bounds__(256) k_rows_to_img(const float *__restrict__ X, int lda, int K, int64_t M, __half *__restrict__ img, int nk) {
+__global__ void __launch_bounds__(256) k_rows_to_img(const float *__restrict__ X, int lda, int K, int64_t M, __half *__restrict__ img, int nk,
+                                                     int onehot_sub) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 8-column chunk per thread
   const int chunks_per_row = nk * 8;
   const int64_t total = ((M + 127) / 128) * 128 * chunks_per_row;
@@ -281,6 +304,10 @@ __global__ void __launch_bounds__(256) k_rows_to_img(const float *__restrict__ X
   for (int i = 0; i < 8; ++i) {
     const int k = ch * 8 + i;
     x[i] = (row < M && k < K) ? __ldg(X + row * (int64_t)lda + k) : 0.f;
+    if (onehot_sub >= 0 && (ch >> 3) == onehot_sub) {          // one-hot(row % 16) at columns t and 16 + t of this sub-tile
+      const int c = (ch & 7) * 8 + i;
+      x[i] = (c < 32 && (c & 15) == (int)(row & 15)) ? 1.f : 0.f;
+    }
   }
   uint4 pk;
   __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]), h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
@@ -324,6 +351,23 @@ __global__ void k_table_sums(const float *__restrict__ table, int ld, float *__r
   if (lane == 0) out[t * 2 + part] = s;
 }
 
+// extended projection weight (N, F+32): [ wp | hi(table)^T | lo(table)^T ] with hi = fp16(table), lo = table - hi
+__global__ void k_build_wp_ext(const float *__restrict__ wp, const float *__restrict__ table, float *__restrict__ out, int N, int F) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = F + 32;
+  if (idx >= N * ld) return;
+  const int n = idx / ld, c = idx % ld;
+  float v;
+  if (c < F) v = wp[(size_t)n * F + c];
+  else {
+    const int t = (c - F) & 15;
+    const float x = table[(size_t)t * N + n];
+    const float hi = __half2float(__float2half_rn(x));
+    v = (c - F) < 16 ? hi : x - hi;
+  }
+  out[idx] = v;
+}
+
 __global__ void k_pad_bias(const float *__restrict__ b, int N, float *__restrict__ out, int Npad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Npad) out[i] = (b && i < N) ? b[i] : 0.f;
@@ -354,17 +398,19 @@ int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw
   return ARX_OK;
 }
 
-int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, cudaStream_t st) {
+int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, int onehot_sub, cudaStream_t st) {
   const int64_t total = ((M + 127) / 128) * 128 * nk * 8;
-  k_rows_to_img<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, lda, K, M, img, nk);
+  k_rows_to_img<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, lda, K, M, img, nk, onehot_sub);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }
 
 // act(A.W^T + b) -> fp16 activation image with c_nk K-sub-tiles per row tile
-int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, cudaStream_t st) {
+int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,
+                      cudaStream_t st) {
   GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.M = M; p.act = act; p.c_img = c_img; p.c_nk = c_nk;
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.a_nk = L.nk; p.M = M; p.act = act; p.c_img = c_img; p.c_nk = c_nk;
+  p.onehot_sub = onehot_sub;
   if (L.BN == 192) return launch_gemm<192, OUT_IMG16>(h, p, L.n_tiles, st);
   if (L.BN == 256) return launch_gemm<256, OUT_IMG16>(h, p, L.n_tiles, st);
   if (L.BN == 64) return launch_gemm<64, OUT_IMG16, 4>(h, p, L.n_tiles, st);     // deep-K layers: 4x the CTAs, 4-stage ring
@@ -372,10 +418,10 @@ int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, 
 }
 
 // A.W^T (+ table[row % T]) -> fp32 row-major
-int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
+int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table, int T,
                       cudaStream_t st) {
   GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = a_nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
   p.table = table; p.T = T;
   if (L.BN == 256) return launch_gemm<256, OUT_F32>(h, p, L.n_tiles, st);
   return arx_fail(h, ARX_ERR_INVALID, "tc_linear_f32: unsupported BN %d", L.BN);
@@ -385,7 +431,7 @@ int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, 
 int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, const float *w3, const float *b3, float *out,
                               cudaStream_t st) {
   GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.M = M; p.act = ARX_ACT_RELU; p.w3 = w3; p.b3 = b3; p.out1 = out;
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.a_nk = L.nk; p.M = M; p.act = ARX_ACT_RELU; p.w3 = w3; p.b3 = b3; p.out1 = out;
   if (L.BN == 64) return launch_gemm<64, OUT_SIGMOID_DOT>(h, p, 1, st);
   return arx_fail(h, ARX_ERR_INVALID, "tc_linear_sigmoid_dot: unsupported BN %d", L.BN);
 }
@@ -403,7 +449,7 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
     slots_set = true;
   }
   GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;
   p.kq_img = kq_img; p.ln_g = ln_g; p.ln_b = ln_b; p.alpha = alpha; p.table_ld = table_ld; p.table_sums = table_sums;
   return launch_gemm<256, OUT_PROJ16>(h, p, 2, st);
 }
@@ -415,11 +461,18 @@ int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *o
 }
 
 // A.W^T + table[row % T] -> fp32 row-major for a narrow (32-column) layer
-int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
-                            cudaStream_t st) {
+int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table,
+                            int T, cudaStream_t st) {
   GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = a_nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
   p.table = table; p.T = T;
   if (L.BN == 32) return launch_gemm<32, OUT_F32>(h, p, L.n_tiles, st);
   return arx_fail(h, ARX_ERR_INVALID, "tc_linear_f32_small: unsupported BN %d", L.BN);
+}
+
+int arx_tc_build_wp_ext(arx_handle *h, const float *wp, const float *table, float *out, int N, int F, cudaStream_t st) {
+  const int total = N * (F + 32);
+  k_build_wp_ext<<<(total + 255) / 256, 256, 0, st>>>(wp, table, out, N, F);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
 }

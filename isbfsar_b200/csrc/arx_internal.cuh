@@ -24,6 +24,8 @@ struct ArxTransformer {
   float *wp = nullptr;      // (2cD, F): K parts then V parts of k_linear/v_linear (model.py:41-44)
   float *bp = nullptr;      // (T, 2cD) table: positional encoding through the projection + biases
   float *bp_sums = nullptr; // (T, 2) row sums of the table over the two K parts
+  float *wp_ext = nullptr;  // (2cD, F+32): wp | hi(table)^T | lo(table)^T -- the table enters the GEMM through one-hot K columns (T == 16)
+  bool table_in_gemm = false;
   float *ln_g = nullptr, *ln_b = nullptr;
   int32_t *tuples = nullptr; // (N,c) int32, built on device
   int32_t *q_slots = nullptr; // (128,2) internal padded-triangular order of the query tuples (T=16 pairs), -1 = pad
@@ -141,9 +143,10 @@ int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *
 
 // ---- tcgen05 GEMM (arx_gemm_tc.cu) ------------------------------------------------
 int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw, const float *bias, int N, int K, int BN, cudaStream_t st);
-int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, cudaStream_t st);
-int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, cudaStream_t st);
-int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
+int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, int onehot_sub, cudaStream_t st);
+int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,
+                      cudaStream_t st);
+int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table, int T,
                       cudaStream_t st);
 int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, const float *w3, const float *b3, float *out,
                               cudaStream_t st);
@@ -181,8 +184,10 @@ int arx_tc2_head_prepare_weights(arx_handle *h, ArxTransformer &tr, cudaStream_t
 int arx_tc2_support_uc(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
 int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *uab, int64_t n_win, const int32_t *chosen,
                         __half *y_img, int y_nk, cudaStream_t st);
-int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, float *C, int ldc, const float *table, int T,
-                            cudaStream_t st);
+int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table,
+                            int T, cudaStream_t st);
+
+int arx_tc_build_wp_ext(arx_handle *h, const float *wp, const float *table, float *out, int N, int F, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);
