@@ -75,7 +75,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.001)
 
     def start(self):
         if self.nv is not None:
@@ -89,6 +89,21 @@ class ClockSampler:
         s = sorted(self.samples)
         med = s[len(s) // 2] if s else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def ncu_traffic_bytes():
+    """DRAM bytes per launch of the attention kernel from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    try:
+        for d in json.load(open(p)):
+            if "k_attn_tc2" in d["Kernel Name"]:
+                scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+                rd = float(d["dram__bytes_read.sum"]) * scale[d["units"]["dram__bytes_read.sum"]]
+                wr = float(d["dram__bytes_write.sum"]) * scale[d["units"]["dram__bytes_write.sum"]]
+                return rd + wr
+    except Exception:
+        pass
+    return None
 
 
 def cpu_port(cfg, sd, support, labels, query, seconds, threads):
@@ -275,7 +290,8 @@ def main():
         peak = peaks["bf16_tflops"]
         roofline = {"bound": "tensor", "kernel": "cross_attention (" + ("tcgen05 fp16" if path == 2 else "fp32 CUDA-core") + ")",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
+                    "traffic": ncu_traffic_bytes() if (path == 2 and B == WINDOWS_PER_GPU) else None, "traffic_unit": "bytes per launch (ncu)",
+                    "peak_source": peaks["source"] + " bf16 burst",
                     "algorithmic_flop_per_launch": B * ATTN_FLOP_PER_WINDOW, "ms_per_launch": attn_ms,
                     "stage_ms_per_step": {k: v / max(1, args.steps) for k, v in stage_ms.items()}}
         cpu = None
