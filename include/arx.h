@@ -136,6 +136,15 @@ ARX_API int arx_debug_attention(arx_handle *h, const float *query_dev, int64_t n
 ARX_API int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows,
                    float *logits_host, float *is_true_host, int32_t *chosen_host);
 
+/* Streaming variant of arx_score_host: returns as soon as the copies and kernels are enqueued on the handle's
+ * internal copy/compute streams; up to ARX_HOST_DEPTH requests may be in flight, so the H2D copy of request i+1
+ * overlaps the scoring of request i.  arx_score_host_wait blocks until request `ticket` (returned by submit)
+ * has landed in the host output buffers.  Host buffers must stay valid (and should be pinned) until then. */
+#define ARX_HOST_DEPTH 2
+ARX_API int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_windows,
+                          float *logits_host, float *is_true_host, int32_t *chosen_host, int64_t *ticket);
+ARX_API int arx_score_host_wait(arx_handle *h, int64_t ticket);
+
 /* MetrABS-style heatmap decode (modules/hpe/hpe.py:108-169 + main.py:103-105):
  *   logits_dev (B,8,8,32+8*32) fp32 -> poses_dev (B,3*n_out) fp32 root-centred,
  *   valid_dev (B) uint8 (0 where the reference returns None, hpe.py:152-153).

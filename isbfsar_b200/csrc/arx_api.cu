@@ -233,6 +233,13 @@ void arx_destroy(arx_handle *h) {
     cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); cudaFree(h->tr[i].tl_uab.w_img); cudaFree(h->tr[i].tl_uab.bias);
     cudaFree(h->tr[i].wc); cudaFree(h->tr[i].tcomp);
   }
+  for (int i = 0; i < ARX_HOST_DEPTH; ++i) {
+    cudaFree(h->hs_in[i]); cudaFree(h->hs_out[i]);
+    if (h->hs_ev_h2d[i]) cudaEventDestroy(h->hs_ev_h2d[i]);
+    if (h->hs_ev_comp[i]) cudaEventDestroy(h->hs_ev_comp[i]);
+    if (h->hs_ev_done[i]) cudaEventDestroy(h->hs_ev_done[i]);
+  }
+  if (h->hs_h2d) { cudaStreamDestroy(h->hs_h2d); cudaStreamDestroy(h->hs_comp); cudaStreamDestroy(h->hs_d2h); }
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_support_done) cudaEventDestroy(h->ev_support_done);
@@ -640,6 +647,8 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, use_tc, tuples32, tcl, tc_head);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
   h->last_path = use_tc ? 2 : 1;
+  if (st != h->hs_comp && h->hs_submitted > 0)      // the shared workspace may still be in use by streamed requests
+    ARX_CUDA(h, cudaStreamWaitEvent(st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0));
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
     const int64_t n = std::min(chunk, n_windows - b0);
     const float *FE;
@@ -681,6 +690,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
     if (use_tc && !fused_proj && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
     if ((rc = support_wait(h, st))) return rc;                   // join the support chain (side stream) before its operands are read
+
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
@@ -797,6 +807,70 @@ int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, fl
   }
   ARX_CUDA(h, cudaStreamSynchronize(h->own_stream[0]));
   ARX_CUDA(h, cudaStreamSynchronize(h->own_stream[1]));
+  return ARX_OK;
+}
+
+int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_windows, float *logits_host, float *is_true_host,
+                          int32_t *chosen_host, int64_t *ticket) {
+  if (!h || !query_host || !logits_host || !ticket || n_windows <= 0) return arx_fail(h, ARX_ERR_INVALID, "score_host_submit: bad argument");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score_host_submit: support set not set");
+  const bool disc = h->cfg.has_discriminator && is_true_host;
+  const int way = h->way;
+  const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);
+  const size_t out_per = (size_t)(way + 2) * sizeof(float);
+  if (!h->hs_h2d) {
+    ARX_CUDA(h, cudaStreamCreateWithFlags(&h->hs_h2d, cudaStreamNonBlocking));
+    ARX_CUDA(h, cudaStreamCreateWithFlags(&h->hs_comp, cudaStreamNonBlocking));
+    ARX_CUDA(h, cudaStreamCreateWithFlags(&h->hs_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < ARX_HOST_DEPTH; ++i) {
+      ARX_CUDA(h, cudaEventCreateWithFlags(&h->hs_ev_h2d[i], cudaEventDisableTiming));
+      ARX_CUDA(h, cudaEventCreateWithFlags(&h->hs_ev_comp[i], cudaEventDisableTiming));
+      ARX_CUDA(h, cudaEventCreateWithFlags(&h->hs_ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (n_windows > h->hs_cap_windows || way != h->hs_way) {
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    for (int i = 0; i < ARX_HOST_DEPTH; ++i) {
+      cudaFree(h->hs_in[i]); cudaFree(h->hs_out[i]);
+      h->hs_in[i] = h->hs_out[i] = nullptr;
+      ARX_CUDA(h, cudaMalloc(&h->hs_in[i], n_windows * in_per));
+      ARX_CUDA(h, cudaMalloc(&h->hs_out[i], n_windows * out_per));
+    }
+    h->hs_cap_windows = n_windows;
+    h->hs_way = way;
+    h->hs_submitted = 0;
+  }
+  const int64_t id = h->hs_submitted;
+  const int s = (int)(id % ARX_HOST_DEPTH);
+  float *din = static_cast<float *>(h->hs_in[s]);
+  float *dlog = static_cast<float *>(h->hs_out[s]);
+  float *dist = dlog + (size_t)n_windows * way;
+  int32_t *dch = reinterpret_cast<int32_t *>(dist + n_windows);
+  // H2D of request id may start once the request that used this slot (id - DEPTH) has been scored
+  if (id >= ARX_HOST_DEPTH) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_h2d, h->hs_ev_comp[s], 0));
+  ARX_CUDA(h, cudaMemcpyAsync(din, query_host, n_windows * in_per, cudaMemcpyHostToDevice, h->hs_h2d));
+  ARX_CUDA(h, cudaEventRecord(h->hs_ev_h2d[s], h->hs_h2d));
+  // scoring: after its inputs arrived and after the results previously held in this slot went back to the host
+  ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_h2d[s], 0));
+  if (h->score_recorded) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->ev_score_done, 0));     // workspace shared with arx_score callers
+  if (id >= ARX_HOST_DEPTH) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_done[s], 0));
+  int rc = score_impl(h, 0, din, nullptr, n_windows, dlog, disc ? dist : nullptr, dch, nullptr, nullptr, h->hs_comp);
+  if (rc) return rc;
+  ARX_CUDA(h, cudaEventRecord(h->hs_ev_comp[s], h->hs_comp));
+  ARX_CUDA(h, cudaStreamWaitEvent(h->hs_d2h, h->hs_ev_comp[s], 0));
+  ARX_CUDA(h, cudaMemcpyAsync(logits_host, dlog, (size_t)n_windows * way * sizeof(float), cudaMemcpyDeviceToHost, h->hs_d2h));
+  if (disc) ARX_CUDA(h, cudaMemcpyAsync(is_true_host, dist, (size_t)n_windows * sizeof(float), cudaMemcpyDeviceToHost, h->hs_d2h));
+  if (chosen_host) ARX_CUDA(h, cudaMemcpyAsync(chosen_host, dch, (size_t)n_windows * sizeof(int32_t), cudaMemcpyDeviceToHost, h->hs_d2h));
+  ARX_CUDA(h, cudaEventRecord(h->hs_ev_done[s], h->hs_d2h));
+  *ticket = id;
+  h->hs_submitted = id + 1;
+  return ARX_OK;
+}
+
+int arx_score_host_wait(arx_handle *h, int64_t ticket) {
+  if (!h || ticket < 0 || ticket >= h->hs_submitted) return arx_fail(h, ARX_ERR_INVALID, "score_host_wait: unknown ticket");
+  if (ticket + ARX_HOST_DEPTH < h->hs_submitted) return ARX_OK;       // its slot has been reused: it completed long ago
+  ARX_CUDA(h, cudaEventSynchronize(h->hs_ev_done[ticket % ARX_HOST_DEPTH]));
   return ARX_OK;
 }
 

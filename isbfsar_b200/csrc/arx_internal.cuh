@@ -81,6 +81,13 @@ struct arx_handle {
   int stage_way = 0;
   cudaStream_t own_stream[2] = {nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  // streaming host path (arx_score_host_submit / _wait)
+  cudaStream_t hs_h2d = nullptr, hs_comp = nullptr, hs_d2h = nullptr;
+  void *hs_in[ARX_HOST_DEPTH] = {nullptr, nullptr};
+  void *hs_out[ARX_HOST_DEPTH] = {nullptr, nullptr};
+  cudaEvent_t hs_ev_h2d[ARX_HOST_DEPTH] = {nullptr, nullptr}, hs_ev_comp[ARX_HOST_DEPTH] = {nullptr, nullptr}, hs_ev_done[ARX_HOST_DEPTH] = {nullptr, nullptr};
+  int64_t hs_cap_windows = 0, hs_submitted = 0;
+  int hs_way = 0;
   int64_t launches = 0;
   // stage timers (arx_profile_*)
   bool prof_on = false;

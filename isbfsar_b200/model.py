@@ -120,6 +120,18 @@ class _LazyPrototypes:
         return iter(self._get())
 
 
+class _HostTicket:
+    """Handle of one in-flight `score_host_async` request (keeps the host buffers alive)."""
+
+    def __init__(self, model, ticket, query, logits, is_true):
+        self._model, self._ticket, self._query, self._logits, self._is_true = model, ticket, query, logits, is_true
+
+    def result(self):
+        m = self._model
+        _lib.check(_lib.load().arx_score_host_wait(m._h, self._ticket), m._h, "arx_score_host_wait")
+        return self._logits, self._is_true
+
+
 class TRXOS(nn.Module):
     """B200-native TRX-OS scorer with the reference API (model.py:219-328)."""
 
@@ -312,21 +324,48 @@ class TRXOS(nn.Module):
                        h, "arx_score")
         return (logits, is_true, chosen) if want_chosen else (logits, is_true)
 
-    def score_host(self, query_cpu):
-        """End to end from HOST memory (pinned for overlap): query (B,T,3J) CPU -> (logits, is_true) CPU tensors."""
+    def _host_out(self, B, way, out):
+        if out is not None:
+            logits, is_true = out
+            assert logits.shape == (B, way) and logits.dtype == torch.float32 and logits.is_contiguous()
+            return logits, is_true
+        logits = torch.empty((B, way), dtype=torch.float32).pin_memory()
+        is_true = torch.empty((B, 1), dtype=torch.float32).pin_memory() if self.model == "DISC" else None
+        return logits, is_true
+
+    def score_host(self, query_cpu, out=None):
+        """End to end from HOST memory (pinned for overlap): query (B,T,3J) CPU -> (logits, is_true) CPU tensors.
+        `out=(logits, is_true)` reuses caller-provided (pinned) result tensors."""
         h = self._ensure()
         lib = _lib.load()
         q = query_cpu
         assert q.device.type == "cpu" and q.dtype == torch.float32 and q.is_contiguous()
         B = q.shape[0]
         way = lib.arx_support_way(h)
-        logits = torch.empty((B, way), dtype=torch.float32).pin_memory()
-        is_true = torch.empty((B, 1), dtype=torch.float32).pin_memory() if self.model == "DISC" else None
+        logits, is_true = self._host_out(B, way, out)
         with torch.cuda.device(self._device()):
             _lib.check(lib.arx_score_host(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
                                           C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None),
                        h, "arx_score_host")
         return logits, is_true
+
+    def score_host_async(self, query_cpu, out=None):
+        """Streaming form of score_host: enqueue and return a ticket object; `ticket.result()` blocks until the
+        (logits, is_true) host tensors are filled.  Up to two requests are kept in flight by the library, so the
+        H2D copy of the next request overlaps the scoring of the current one."""
+        h = self._ensure()
+        lib = _lib.load()
+        q = query_cpu
+        assert q.device.type == "cpu" and q.dtype == torch.float32 and q.is_contiguous()
+        B = q.shape[0]
+        way = lib.arx_support_way(h)
+        logits, is_true = self._host_out(B, way, out)
+        t = C.c_int64()
+        with torch.cuda.device(self._device()):
+            _lib.check(lib.arx_score_host_submit(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
+                                                 C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None,
+                                                 C.byref(t)), h, "arx_score_host_submit")
+        return _HostTicket(self, int(t.value), q, logits, is_true)
 
     def score_features(self, ti, qfeats):
         """`transformers[ti](support, labels, queries)['logits']` from frame features (B,T,F)."""

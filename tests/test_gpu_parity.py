@@ -376,3 +376,28 @@ def test_kernel_variants_agree(variant):
     logits, is_true = m.score(torch.from_numpy(query).cuda())
     assert m.last_path() == 2
     assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
+
+
+def test_streaming_host_api_matches_device_path():
+    """arx_score_host_submit/_wait: several requests in flight, interleaved with blocking and device-side calls and a
+    support-set change; every result equals the device path bit for bit."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 700, 101, "structured")
+    S = torch.from_numpy(support[0]).cuda()
+    m.set_support(poses=S)
+    qs = [torch.from_numpy(query[i * 100:(i + 1) * 100 + 37 * (i % 2)]).pin_memory() for i in range(6)]   # ragged sizes
+    tickets = [m.score_host_async(q) for q in qs[:3]]
+    dev = [m.score(q.cuda()) for q in qs]                       # device-side calls share the workspace with the streamed ones
+    tickets += [m.score_host_async(q) for q in qs[3:]]
+    blocking = m.score_host(qs[0])
+    for q, t, d in zip(qs, tickets, dev):
+        lo, it = t.result()
+        assert torch.equal(lo, d[0].cpu()) and torch.equal(it, d[1].cpu())
+    assert torch.equal(blocking[0], dev[0][0].cpu())
+    # change the support set while nothing is in flight, stream again
+    m.set_support(poses=S.flip(0))
+    t = m.score_host_async(qs[1])
+    lo, it = t.result()
+    ref = m.score(qs[1].cuda())
+    assert torch.equal(lo, ref[0].cpu()) and torch.equal(lo, dev[1][0].cpu().flip(1))
