@@ -186,7 +186,7 @@ def main():
     import torch.distributed as dist
     from oracle.synth import Cfg, make_episode, make_state_dict
     from tests.util import make_model
-    from isbfsar_b200.dist import broadcast_support, gather_scores
+    from isbfsar_b200.dist import ScoreGatherer, broadcast_support
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,21 +210,33 @@ def main():
     s_dev = torch.from_numpy(support0[0]).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)           # > 126 MB L2
 
-    def step(first=False):
-        if first or not args.static_support:
-            if rank == 0:
-                model.set_support(poses=s_dev)
-            if world > 1:
-                broadcast_support(model, WAY, src=0, device=dev)
-        logits, is_true = model.score(q_dev)
-        if world > 1:
-            logits, is_true = gather_scores(logits, is_true, B * world)
-        return logits, is_true
+    gatherer = ScoreGatherer(B, WAY, True, dev)
+
+    def step():
+        # every rank processes the (replicated) support poses itself -- asynchronously on the scorer's side stream,
+        # exactly as at N=1 -- scores its own shard, and the scores are all-gathered (one NCCL call per batch)
+        if not args.static_support:
+            model.set_support(poses=s_dev)
+        model.score(q_dev, out=gatherer.out())
+        return gatherer.gather()
+
+    # once, before timing (north_star: "broadcast the support-set tuple embeddings once"): rank 0 processes the support
+    # set and NCCL-broadcasts the tuple embeddings; the other ranks import them and must reproduce their own local result
+    model.set_support(poses=s_dev)
+    ref_logits, ref_true = model.score(q_dev)
+    if world > 1:
+        broadcast_support(model, WAY, src=0, device=dev)
+        torch.cuda.synchronize()
+        got_logits, got_true = model.score(q_dev)
+        if not (torch.equal(got_logits, ref_logits) and torch.equal(got_true, ref_true)):
+            raise SystemExit("bench: scores with NCCL-broadcast support embeddings differ from locally computed ones")
+        model.set_support(poses=s_dev)
 
     # correctness guard on the exact tensors being timed (oracle = checker only, small subset)
-    logits, is_true = step(first=True)
+    per_rank = step()
     torch.cuda.synchronize()
-    mine = logits[rank * B: rank * B + 32].cpu().numpy() if world > 1 else logits[:32].cpu().numpy()
+    logits = per_rank[rank][0]
+    mine = logits[:32].cpu().numpy()
     from oracle.trx_oracle import TrxOracle
     lo, it = TrxOracle(cfg, sd).score(support0, labels, query[:32])
     err = float(np.abs(mine / lo - 1).max())
@@ -258,11 +270,10 @@ def main():
     launches = model.launch_count() - l0
     clocks = sampler.stop()
 
+    model.set_support(poses=s_dev)
     # end to end through the host-buffer entry points: pinned H2D of the windows + D2H of the scores, every step.
     #  (a) streaming: arx_score_host_submit/_wait with two requests in flight (what a frame-streaming caller does);
     #  (b) blocking:  one arx_score_host call at a time.
-    if rank == 0:
-        model.set_support(poses=s_dev)
     outs = [(torch.empty((B, WAY), dtype=torch.float32).pin_memory(), torch.empty((B, 1), dtype=torch.float32).pin_memory())
             for _ in range(3)]
     for _ in range(2):
@@ -291,8 +302,7 @@ def main():
         tk.result()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_check = float((outs[(e2e_steps - 1) % 3][0] - logits[rank * B: rank * B + B].cpu() if world > 1
-                       else outs[(e2e_steps - 1) % 3][0] - logits.cpu()).abs().max())
+    e2e_check = float((outs[(e2e_steps - 1) % 3][0] - ref_logits.cpu()).abs().max())
 
     t = torch.tensor([total_ms, e2e_s, float(launches), e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -326,8 +336,9 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16" if path == 2 else "f32", "data": "synthetic",
                 "config": {"workload": f"cfg2: {B} query windows per GPU x 5-way 1-shot, T=16, J=30, pair tuples (N=120); "
-                                       + ("step = score shard + gather scores (support set once, --static-support)" if args.static_support
-                                          else "step = set/broadcast support + score shard + gather scores"),
+                                       + ("step = score shard + all-gather scores (support set processed once, --static-support)" if args.static_support
+                                          else "step = process support set (every rank, replicated poses) + score shard + all-gather scores; "
+                                               "NCCL broadcast of the support tuple embeddings done and verified once before timing"),
                            "l2": "flushed between timed steps (256 MiB write)", "path": path,
                            "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
                 "clocks": clocks,

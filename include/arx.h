@@ -106,8 +106,10 @@ ARX_API int arx_set_support_features(arx_handle *h, const float *feats_dev, int3
 ARX_API int arx_get_support_features(arx_handle *h, float *feats_dev, void *stream);
 ARX_API int arx_support_way(const arx_handle *h);
 
-/* Support operands as one flat device blob, for NCCL broadcast across ranks
- * (SURVEY.md 8e).  export/import must use handles with identical config+weights. */
+/* Support-set tuple embeddings (LayerNorm-ed K and V tuple tensors of every transformer, fp32) as one flat device
+ * blob, for the NCCL broadcast across ranks.  export/import must use handles with identical
+ * config+weights.  import rebuilds the tensor-core operand images on the handle's side stream; a handle that
+ * imported its support set cannot return 'support_features' (arx_get_support_features -> ARX_ERR_STATE). */
 ARX_API int64_t arx_support_blob_bytes(const arx_handle *h, int32_t way);
 ARX_API int arx_export_support(arx_handle *h, void *blob_dev, void *stream);
 ARX_API int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *stream);

@@ -498,6 +498,7 @@ int arx_set_support_poses(arx_handle *h, const float *poses_dev, int32_t way, vo
   const int64_t rows = (int64_t)way * h->T;
   if ((rc = support_wait(h, st))) return rc;                       // a previous chain may still be reading ss_poses
   ARX_CUDA(h, cudaMemcpyAsync(h->ss_poses, poses_dev, (size_t)rows * h->J3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->ss_poses_valid = true;
   cudaStream_t ss;
   if ((rc = support_fork(h, st, &ss))) return rc;                  // the caller's buffer is not touched past this point
   if (h->tc_linears) {
@@ -524,6 +525,8 @@ static int support_features_materialise(arx_handle *h, cudaStream_t st) {
   int rcw = support_wait(h, st);
   if (rcw) return rcw;
   if (h->ss_feat_valid) return ARX_OK;
+  if (!h->ss_poses_valid)
+    return arx_fail(h, ARX_ERR_STATE, "support features are not available: this handle received the support operands through arx_import_support");
   int rc = arx_embed(h, h->ss_poses, (int64_t)h->way * h->T, h->ss_feat, st);      // fp32 MLP (model.py:175-180)
   if (rc == ARX_OK) h->ss_feat_valid = true;
   return rc;
@@ -543,23 +546,21 @@ int arx_support_way(const arx_handle *h) { return h ? h->way : ARX_ERR_INVALID; 
 
 int64_t arx_support_blob_bytes(const arx_handle *h, int32_t way) {
   if (!h || way < 1) return ARX_ERR_INVALID;
-  int64_t n = (int64_t)way * h->T * h->F;
-  for (int i = 0; i < h->cfg.n_transformers; ++i) n += 2ll * way * h->tr[i].N * h->D;
+  int64_t n = 0;
+  for (int i = 0; i < h->cfg.n_transformers; ++i) n += 2ll * way * h->tr[i].N * h->D;      // K (LayerNorm-ed) and V tuple tensors
   return n * (int64_t)sizeof(float);
 }
 
+// blob = for every transformer [ks (way,N,D) | vs (way,N,D)] fp32: the support-set tuple embeddings
 int arx_export_support(arx_handle *h, void *blob_dev, void *stream) {
   if (!h || !blob_dev) return arx_fail(h, ARX_ERR_INVALID, "export_support: bad argument");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "export_support: no support set");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rcm = support_features_materialise(h, st);
-  if (rcm) return rcm;
+  int rc = support_wait(h, st);                       // the chain that produces ks/vs runs on the side stream
+  if (rc) return rc;
   float *p = static_cast<float *>(blob_dev);
-  size_t n = (size_t)h->way * h->T * h->F;
-  ARX_CUDA(h, cudaMemcpyAsync(p, h->ss_feat, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  p += n;
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
-    n = (size_t)h->way * h->tr[i].N * h->D;
+    const size_t n = (size_t)h->way * h->tr[i].N * h->D;
     ARX_CUDA(h, cudaMemcpyAsync(p, h->tr[i].ks, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p += n;
     ARX_CUDA(h, cudaMemcpyAsync(p, h->tr[i].vs, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -572,30 +573,29 @@ int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *s
   if (!h || !blob_dev || way < 1) return arx_fail(h, ARX_ERR_INVALID, "import_support: bad argument");
   if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "import_support: weights not loaded");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  {
-    int rca = support_alloc(h, way, st);
-    if (rca) return rca;
-  }
-  {
-    int rcw = support_wait(h, st);
-    if (rcw) return rcw;
-  }
-  h->ss_feat_valid = true;
+  int rc = support_alloc(h, way, st);
+  if (rc) return rc;
+  // like set_support: the copies and the operand-image builds run on the side stream (after everything queued on
+  // `st`, i.e. after the collective that filled the blob), overlapped with the query-side kernels of the next score
+  cudaStream_t ss;
+  if ((rc = support_fork(h, st, &ss))) return rc;
+  h->ss_feat_valid = false;
+  h->ss_poses_valid = false;
   const float *p = static_cast<const float *>(blob_dev);
-  size_t n = (size_t)way * h->T * h->F;
-  ARX_CUDA(h, cudaMemcpyAsync(h->ss_feat, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  p += n;
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
-    n = (size_t)way * h->tr[i].N * h->D;
-    ARX_CUDA(h, cudaMemcpyAsync(h->tr[i].ks, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ArxTransformer &tr = h->tr[i];
+    const size_t n = (size_t)way * tr.N * h->D;
+    ARX_CUDA(h, cudaMemcpyAsync(tr.ks, p, n * sizeof(float), cudaMemcpyDeviceToDevice, ss));
     p += n;
-    ARX_CUDA(h, cudaMemcpyAsync(h->tr[i].vs, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ARX_CUDA(h, cudaMemcpyAsync(tr.vs, p, n * sizeof(float), cudaMemcpyDeviceToDevice, ss));
     p += n;
-    int rc2;
-    if (h->cfg.force_path != 1 && arx_tc_supported(h, h->tr[i]) && (rc2 = arx_tc_prep_support(h, h->tr[i], way, st))) return rc2;
+    if (h->cfg.force_path != 1 && arx_tc_supported(h, tr)) {
+      if ((rc = arx_tc_prep_support(h, tr, way, ss))) return rc;
+      if (i == 0 && h->tc_linears && h->cfg.has_discriminator && h->T == 16 && tr.c == 2 && (rc = arx_tc2_support_uc(h, tr, way, ss))) return rc;
+    }
   }
   h->way = way;
-  return ARX_OK;
+  return support_join_record(h);
 }
 
 static int prof_mark(arx_handle *h, int idx, cudaStream_t st) {

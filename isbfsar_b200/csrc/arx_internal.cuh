@@ -68,6 +68,7 @@ struct arx_handle {
   cudaEvent_t ev_fork = nullptr, ev_support_done = nullptr, ev_score_done = nullptr;
   bool support_recorded = false, score_recorded = false;
   float *ss_poses = nullptr;       // copy of the support poses when the features were produced on tensor cores
+  bool ss_poses_valid = false;
   bool ss_feat_valid = false;      // ss_feat holds fp32 features (else they are derived lazily from ss_poses)
   // workspace (grown on demand)
   void *ws = nullptr;

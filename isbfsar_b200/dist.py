@@ -24,19 +24,38 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+_comm_streams = {}
+_blobs = {}
+
+
 def broadcast_support(scorer, way: int, src: int = 0, group=None, device=None) -> None:
-    """Rank `src` has called set_support for `way` classes; every other rank receives the operands.
-    `way` must be passed identically on every rank (no metadata exchange, no host synchronisation)."""
+    """Rank `src` has called set_support for `way` classes; every other rank receives the support-set tuple
+    embeddings.  `way` must be passed identically on every rank (no metadata exchange, no host synchronisation).
+    On CUDA the export, the collective and the import run on a dedicated communication stream, so the query-side
+    kernels of the next `score` overlap them; the scorer joins on its own event before it reads the operands."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     rank = dist.get_rank(group)
-    if rank == src:
-        blob = scorer.export_support()
-    else:
-        blob = torch.empty((scorer.support_blob_numel(way),), dtype=torch.float32, device=device)
-    dist.broadcast(blob, src=src, group=group)
-    if rank != src:
-        scorer.import_support(blob, way)
+    n = scorer.support_blob_numel(way)
+    on_cuda = device is not None and torch.device(device).type == "cuda"
+    if not on_cuda:
+        blob = scorer.export_support() if rank == src else torch.empty((n,), dtype=torch.float32, device=device)
+        dist.broadcast(blob, src=src, group=group)
+        if rank != src:
+            scorer.import_support(blob, way)
+        return
+    key = (torch.device(device), n)
+    if key not in _blobs:                     # persistent buffer: it is touched by another stream than the allocating one
+        _blobs[key] = torch.empty((n,), dtype=torch.float32, device=device)
+        _comm_streams[torch.device(device)] = torch.cuda.Stream(device=device)
+    blob, comm = _blobs[key], _comm_streams[torch.device(device)]
+    comm.wait_stream(torch.cuda.current_stream(device))      # set_support was issued on the current stream
+    with torch.cuda.stream(comm):
+        if rank == src:
+            scorer.export_support(out=blob)
+        dist.broadcast(blob, src=src, group=group)
+        if rank != src:
+            scorer.import_support(blob, way)
 
 
 def gather_scores(logits: torch.Tensor, is_true, n_total: int, group=None):
@@ -63,6 +82,34 @@ def gather_scores(logits: torch.Tensor, is_true, n_total: int, group=None):
         out3 = out.view(world, mx, cols)
         full = torch.cat([out3[r, : shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0]] for r in range(world)])
     return full[:, :way], (full[:, way:] if is_true is not None else None)
+
+
+class ScoreGatherer:
+    """Preallocated all-gather of equal shards: every rank scores `n_local` windows straight into its slot of a
+    flat `[logits (n_local*way) | is_true (n_local)]` buffer; one `all_gather_into_tensor` per batch, no copies."""
+
+    def __init__(self, n_local: int, way: int, has_is_true: bool, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_local, self.way, self.has_is_true = n_local, way, has_is_true
+        self.per = n_local * (way + (1 if has_is_true else 0))
+        self.local = torch.empty((self.per,), dtype=torch.float32, device=device)
+        self.all = torch.empty((self.world * self.per,), dtype=torch.float32, device=device) if self.world > 1 else self.local
+
+    def _views(self, flat):
+        lo = flat[: self.n_local * self.way].view(self.n_local, self.way)
+        it = flat[self.n_local * self.way:].view(self.n_local, 1) if self.has_is_true else None
+        return lo, it
+
+    def out(self):
+        """(logits, is_true) views of this rank's slot: pass as `out=` to `scorer.score`."""
+        return self._views(self.local)
+
+    def gather(self):
+        """-> list over ranks of (logits (n_local,way), is_true (n_local,1)) views of the gathered buffer."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.all, self.local, group=self.group)
+        return [self._views(self.all[r * self.per:(r + 1) * self.per]) for r in range(self.world)]
 
 
 def score_sharded(scorer, query_full_or_local, n_total: int, local: bool = False, group=None):

@@ -302,8 +302,9 @@ class TRXOS(nn.Module):
                        "arx_get_support_features")
         return out
 
-    def score(self, query, want_chosen=False):
-        """query (B,T,3J) on the model's device -> logits (B,W), is_true (B,1) [None without DISC]."""
+    def score(self, query, want_chosen=False, out=None):
+        """query (B,T,3J) on the model's device -> logits (B,W), is_true (B,1) [None without DISC].
+        `out=(logits, is_true)` writes into caller-provided contiguous float32 CUDA tensors."""
         h = self._ensure()
         dev = self._device()
         lib = _lib.load()
@@ -312,8 +313,13 @@ class TRXOS(nn.Module):
         way = lib.arx_support_way(h)
         if way < 1:
             raise RuntimeError("score: support set not set")
-        logits = torch.empty((B, way), dtype=torch.float32, device=dev)
-        is_true = torch.empty((B, 1), dtype=torch.float32, device=dev) if self.model == "DISC" else None
+        if out is not None:
+            logits, is_true = out
+            assert logits.shape == (B, way) and logits.is_contiguous() and logits.dtype == torch.float32 and logits.device == dev
+            assert is_true is None or (is_true.numel() == B and is_true.is_contiguous() and is_true.dtype == torch.float32)
+        else:
+            logits = torch.empty((B, way), dtype=torch.float32, device=dev)
+            is_true = torch.empty((B, 1), dtype=torch.float32, device=dev) if self.model == "DISC" else None
         chosen = torch.empty((B,), dtype=torch.int32, device=dev) if want_chosen else None
         if B == 0:
             return (logits, is_true, chosen) if want_chosen else (logits, is_true)
@@ -493,15 +499,16 @@ class TRXOS(nn.Module):
         return None
 
     # ------------------------------------------------------------------ multi-GPU plumbing
-    def export_support(self):
-        """Support operands as one flat float32 CUDA tensor (for `torch.distributed.broadcast`)."""
+    def export_support(self, out=None):
+        """Support-set tuple embeddings as one flat float32 CUDA tensor (for `torch.distributed.broadcast`)."""
         h = self._ensure()
         lib = _lib.load()
         way = lib.arx_support_way(h)
         if way < 1:
             raise RuntimeError("export_support: support set not set")
         n = int(lib.arx_support_blob_bytes(h, way))
-        blob = torch.empty((n // 4,), dtype=torch.float32, device=self._device())
+        blob = out if out is not None else torch.empty((n // 4,), dtype=torch.float32, device=self._device())
+        assert blob.numel() == n // 4 and blob.dtype == torch.float32 and blob.is_contiguous()
         with torch.cuda.device(self._device()):
             _lib.check(lib.arx_export_support(h, C.c_void_p(blob.data_ptr()), self._stream()), h, "arx_export_support")
         return blob
@@ -512,7 +519,7 @@ class TRXOS(nn.Module):
 
     def import_support(self, blob, way):
         h = self._ensure()
-        b = self._f32c(blob, self._device())
+        b = self._f32c(blob, self._device())          # no copy for a contiguous float32 CUDA tensor: the caller keeps it alive
         assert b.numel() == self.support_blob_numel(way)
         with torch.cuda.device(self._device()):
             _lib.check(_lib.load().arx_import_support(h, C.c_void_p(b.data_ptr()), way, self._stream()), h,

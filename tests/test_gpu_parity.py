@@ -401,3 +401,22 @@ def test_streaming_host_api_matches_device_path():
     lo, it = t.result()
     ref = m.score(qs[1].cuda())
     assert torch.equal(lo, ref[0].cpu()) and torch.equal(lo, dev[1][0].cpu().flip(1))
+
+
+def test_export_import_support_roundtrip():
+    """The NCCL payload: tuple embeddings exported from one handle and imported into another (same weights) give
+    bit-identical scores; the importing handle cannot serve 'support_features'."""
+    cfg = Cfg()
+    m1, sd = make_model(cfg, 0)
+    m2, _ = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 200, 111, "structured")
+    Q = torch.from_numpy(query).cuda()
+    m1.set_support(poses=torch.from_numpy(support[0]).cuda())
+    blob = m1.export_support()
+    assert blob.numel() == 2 * 5 * 120 * 128
+    m2.import_support(blob, 5)
+    a, b = m1.score(Q)
+    c, d = m2.score(Q)
+    assert m2.last_path() == 2 and torch.equal(a, c) and torch.equal(b, d)
+    with pytest.raises(RuntimeError):
+        m2.support_features()
