@@ -75,7 +75,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv is not None:
@@ -250,7 +250,8 @@ def main():
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:            # one sampler per job: the ranks share few host cores
+        sampler.start()
     model.profile(True)
     model.profile_read(reset=True)
     l0 = model.launch_count()
