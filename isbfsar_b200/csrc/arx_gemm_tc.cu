@@ -65,11 +65,13 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
     for (int i = 0; i < 2 * NST + 1; ++i) mbar_init(&bars[i], 1);
     mbar_init_fence();
   }
+  pdl_trigger();
   if (warp == 5) { tmem_alloc(tmem_slot, TM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                       // everything above overlapped the previous kernel's tail
 
   if (warp == 4) {
     if (elect_one()) {
@@ -293,6 +295,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 // fp32 row-major [M][lda] (K valid columns) -> fp16 activation image [ceil(M/128)][nk][128 x 64]; zero padded.
 __global__ void __launch_bounds__(256) k_rows_to_img(const float *__restrict__ X, int lda, int K, int64_t M, __half *__restrict__ img, int nk,
                                                      int onehot_sub) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // one 8-column chunk per thread
   const int chunks_per_row = nk * 8;
   const int64_t total = ((M + 127) / 128) * 128 * chunks_per_row;
@@ -378,8 +382,8 @@ template <int BN, int OUT, int NST = 2> int launch_gemm(arx_handle *h, const Gem
   auto kern = k_gemm_tc<BN, OUT, NST>;
   ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((p.M + 127) / 128), (unsigned)n_tiles);
-  kern<<<grid, G_THREADS, smem, st>>>(p);
-  ARX_LAUNCH_CHECK(h);
+  ARX_CUDA(h, arx_launch_pdl(kern, grid, dim3(G_THREADS), smem, st, h->pdl, p));
+  h->launches++;
   return ARX_OK;
 }
 
@@ -400,8 +404,8 @@ int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw
 
 int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, int onehot_sub, cudaStream_t st) {
   const int64_t total = ((M + 127) / 128) * 128 * nk * 8;
-  k_rows_to_img<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, lda, K, M, img, nk, onehot_sub);
-  ARX_LAUNCH_CHECK(h);
+  ARX_CUDA(h, arx_launch_pdl(k_rows_to_img, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, h->pdl, X, lda, K, M, img, nk, onehot_sub));
+  h->launches++;
   return ARX_OK;
 }
 

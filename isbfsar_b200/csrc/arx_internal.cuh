@@ -98,6 +98,7 @@ struct arx_handle {
   int64_t prof_chunks = 0;
   int last_path = 0;
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
+  bool pdl = false;     // programmatic dependent launch for the arx_score kernel chain (debug key 2; measured: no gain, off by default)
   int tc_variant = 0;   // debug: bit 0 selects the K-major P layout
   std::string err;
 };
@@ -117,6 +118,19 @@ int arx_fail(arx_handle *h, int code, const char *fmt, ...);
   } while (0)
 
 int arx_ws_reserve(arx_handle *h, size_t bytes);
+
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in the stream is
+// still running; it must execute griddepcontrol.wait before touching the predecessor's output.
+template <class... KArgs, class... Args>
+static inline cudaError_t arx_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---- fp32 generic kernels (arx_fp32.cu) ------------------------------------------
 enum ArxAct { ARX_ACT_NONE = 0, ARX_ACT_RELU = 1, ARX_ACT_SIGMOID = 2 };

@@ -524,6 +524,8 @@ __global__ void __launch_bounds__(256) k_support_build(const float *__restrict__
 
 __global__ void k_finish_tc(const float *__restrict__ partial, float *__restrict__ logits, int32_t *__restrict__ chosen, int64_t n_win,
                             int way, int N) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_win) return;
   float best = -INFINITY;
@@ -915,8 +917,9 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
   if (mode0 && arx_tc_slot_order(h, tr)) {
     int rc = arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st);
     if (rc) return rc;
-    k_finish_tc<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
-    ARX_LAUNCH_CHECK(h);
+    ARX_CUDA(h, arx_launch_pdl(k_finish_tc, dim3((unsigned)((n_win + 127) / 128)), dim3(128), 0, st, h->pdl, (const float *)partial, logits, chosen,
+                               (int64_t)n_win, way, tr.N));
+    h->launches++;
     return ARX_OK;
   }
   const int groups = (int)((n_win + GROUP - 1) / GROUP);

@@ -120,12 +120,14 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_attn_tc2(const Attn2Params p) 
     mbar_init(&bars[B_P_FULL], 128); mbar_init(&bars[B_P_EMPTY], 1); mbar_init(&bars[B_P_EMPTY1], 1);
     mbar_init_fence();
   }
+  pdl_trigger();
   if (warp == 3) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t TM_S = tmem, TM_O = tmem + 256;
+  pdl_wait();
 
   if (warp < 4) {
     setmaxnreg_dec<40>();
@@ -360,8 +362,8 @@ int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
   const int groups = (int)((n_win + GROUP - 1) / GROUP);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
   ARX_CUDA(h, cudaFuncSetAttribute(k_attn_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  k_attn_tc2<<<grid, NTHREADS2, SMEM_BYTES, st>>>(p);
-  ARX_LAUNCH_CHECK(h);
+  ARX_CUDA(h, arx_launch_pdl(k_attn_tc2, dim3(grid), dim3(NTHREADS2), SMEM_BYTES, st, h->pdl, p));
+  h->launches++;
   return ARX_OK;
 }
 
@@ -416,12 +418,14 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
     }
     mbar_init_fence();
   }
+  pdl_trigger();
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t TM_S = tmem, TM_Y = tmem + 256;
+  pdl_wait();
 
   if (warp < 4) {
     setmaxnreg_dec<40>();
@@ -660,7 +664,7 @@ int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *k
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.uc_img = tr.uc_img; p.uab = uab; p.chosen = chosen; p.y_img = y_img; p.n_win = (int)n_win; p.y_nk = y_nk;
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
   ARX_CUDA(h, cudaFuncSetAttribute(k_head2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H2_SMEM_BYTES));
-  k_head2_tc<<<grid, NTHREADS2, H2_SMEM_BYTES, st>>>(p);
-  ARX_LAUNCH_CHECK(h);
+  ARX_CUDA(h, arx_launch_pdl(k_head2_tc, dim3(grid), dim3(NTHREADS2), H2_SMEM_BYTES, st, h->pdl, p));
+  h->launches++;
   return ARX_OK;
 }
