@@ -98,6 +98,7 @@ struct arx_handle {
   int64_t prof_chunks = 0;
   int last_path = 0;
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
+  int attn_stagger = 1000;   // clocks softmax group 1 starts behind group 0 in k_attn_tc3 (debug key 3)
   bool pdl = false;     // programmatic dependent launch for the arx_score kernel chain (debug key 2; measured: no gain, off by default)
   int tc_variant = 0;   // debug: bit 0 selects the K-major P layout
   std::string err;
@@ -210,6 +211,9 @@ int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a
                             int T, cudaStream_t st);
 
 int arx_tc_build_wp_ext(arx_handle *h, const float *wp, const float *table, float *out, int N, int F, cudaStream_t st);
+
+int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
+                             float *partial, int g_ld, int g_voff, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

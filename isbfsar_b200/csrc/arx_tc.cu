@@ -915,7 +915,9 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
   const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_attention: generic epilogue needs Vq");
   if (mode0 && arx_tc_slot_order(h, tr)) {
-    int rc = arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st);
+    // third-generation kernel by default; variant bit 7 (128) selects the second generation
+    int rc = (variant & 128) ? arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st)
+                             : arx_tc3_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st);
     if (rc) return rc;
     ARX_CUDA(h, arx_launch_pdl(k_finish_tc, dim3((unsigned)((n_win + 127) / 128)), dim3(128), 0, st, h->pdl, (const float *)partial, logits, chosen,
                                (int64_t)n_win, way, tr.N));
