@@ -108,7 +108,7 @@ Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, b
   w.uab = (tcl && tc_head && disc) ? c.take<float>(rows_pad * 32) : nullptr;
   w.H1 = (from_frames && !tcl) ? c.take<float>(n * h->T * h->H) : nullptr;
   w.FE = (from_frames && !tcl) ? c.take<float>(n * h->T * h->F) : nullptr;
-  w.G = c.take<float>(n * h->T * 2 * tr.c * h->D);
+  w.G = c.take<float>((tc ? rows_pad : n * h->T) * 2 * tr.c * h->D);     // chunked layout holds whole 128-row tiles
   w.Kq = tuples32 ? c.take<float>(n * tr.N * h->D) : nullptr;
   w.Vq = tuples32 ? c.take<float>(n * tr.N * h->D) : nullptr;
   w.Z = tuples32 ? c.take<float>(n * way * tr.N * 2) : nullptr;
@@ -635,10 +635,15 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const bool tuples32 = !use_tc || (disc && !tc_head) || !mode0;    // fp32 tuple tensors: fp32 path/head pass, generic epilogue
   const bool tcl = use_tc && h->tc_linears && (h->tc_variant & 4) == 0;
   // fused projection epilogue (Kq images + compact V projections): T=16 pairs, slot order, no fp32 tuple tensors needed
-  const bool fused_proj = tcl && mode0 && arx_tc_slot_order(h, tr) && !tuples32 && (h->tc_variant & 16) == 0;
+  const bool fused_proj = tcl && mode0 && tr.table_in_gemm && arx_tc_slot_order(h, tr) && !tuples32 && (h->tc_variant & 16) == 0;
   const bool head2 = fused_proj && tc_head && ti == 0 && h->tr[0].uc_img != nullptr && (h->tc_variant & 32) == 0;   // second-generation head pass
-  const int g_ld = fused_proj ? 2 * h->D : 2 * tr.c * h->D;      // row stride of G as the attention epilogues see it
-  const int g_voff = fused_proj ? 0 : tr.c * h->D;
+  // default: persistent GEMM -> chunked fp32 projections, then the thread-per-tuple image kernel; the in-GEMM tuple
+  // epilogue (variant bit 9) and the older attention / head kernels (bits 3, 5, 7) read row-major projections
+  const bool split_proj = fused_proj && (h->tc_variant & (512 | 128 | 32 | 8)) == 0 && arx_tcp_supported(tr.tl_proj);
+  const int g_ld = (fused_proj && !split_proj) ? 2 * h->D : 2 * tr.c * h->D;      // row stride of G as the attention epilogues see it
+  const int g_voff = (fused_proj && !split_proj) ? 0 : tr.c * h->D;
+  const bool big_batch = n_windows * h->T >= 128ll * 2 * h->sm_count;             // persistent GEMMs pay off from ~2 tiles per SM
+  const bool p_embed = tcl && big_batch && (h->tc_variant & 1024) == 0 && arx_tcp_supported(h->tl_fc1) && arx_tcp_supported(h->tl_fc2);
   const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32, tcl, tc_head);
   Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32, tcl, tc_head);
   size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
@@ -660,8 +665,13 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
       FE = nullptr;
       if (from_frames) {
         if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
-        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
-        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
+        if (p_embed) {
+          if ((rc = arx_tcp_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
+          if ((rc = arx_tcp_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
+        } else {
+          if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
+          if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
+        }
       } else {
         if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, f_nk, f_onehot, st))) return rc;
       }
@@ -670,8 +680,11 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         int32_t slots[256];
         arx_tc2_slot_table(slots);
         const float alpha = (h->tc_variant & 64) ? -1.f : ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);   // bit 6: timing-only, skip the tuple build
-        if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G,
-                                       tr.table_in_gemm ? nullptr : tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
+        if (split_proj) {
+          if ((rc = arx_tcp_linear_chunked(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, st))) return rc;
+          if (alpha > 0.f && (rc = arx_tuple_img(h, tr, w.G, 2 * tr.c * h->D / 32, n, w.kq_img, alpha, st))) return rc;
+        } else if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G,
+                                              tr.table_in_gemm ? nullptr : tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
           return rc;
         if (head2 && (rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows, w.uab, 32, tr.tcomp, h->T, st))) return rc;
       } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, 2 * tr.c * h->D, tr.table_in_gemm ? nullptr : tr.bp, h->T, st)))
@@ -696,7 +709,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
     if (use_tc) {
       if ((rc = arx_tc_attention(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, w.partial, logits_dev + b0 * way, ch,
-                                 h->tc_variant, g_ld, g_voff, st)))
+                                 h->tc_variant, g_ld, g_voff, split_proj, st)))
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
       if (disc && head2) {

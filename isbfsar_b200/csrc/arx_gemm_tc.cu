@@ -15,6 +15,8 @@ using namespace ptx;
 
 constexpr uint32_t A_SUB = 128 * 128;       // 128 rows x 64 fp16
 constexpr int G_THREADS = 192;
+constexpr uint32_t PROJ_STG = 16 * 260 * 4;                 // one staged window of the fused projection epilogue (padded rows)
+constexpr uint32_t PROJ_EPI = 32768 + 4 * PROJ_STG + 1024;  // image + 4 staged windows + LayerNorm affine
 
 enum { OUT_IMG16 = 0, OUT_F32 = 1, OUT_SIGMOID_DOT = 2, OUT_PROJ16 = 3 };
 
@@ -57,8 +59,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
   constexpr uint32_t TM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * STAGE);     // full[NST], empty[NST], acc
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NST * STAGE + (2 * NST + 1) * 8);
+  constexpr uint32_t BAR_OFF = (OUT == OUT_PROJ16 && PROJ_EPI > NST * STAGE) ? PROJ_EPI : NST * STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + BAR_OFF);     // full[NST], empty[NST], acc
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + BAR_OFF + (2 * NST + 1) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   if (threadIdx.x == 0) {
@@ -112,20 +115,22 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
     float dot = 0.f;
     if constexpr (OUT == OUT_PROJ16) {
       if (nt == 0) {
-        // ---- K parts: this warp owns rows 32w..32w+31 = two whole windows of 16 frames.  Per window: stage the
-        // 16 x 256 fp32 frame projections in shared memory (the operand stages are idle now), then build the
-        // 128 tuple rows K = LN(Gk1[i] + Gk2[j]) * alpha -> fp16 -> swizzled Kq image  (model.py:69-82).
-        float *ws = reinterpret_cast<float *>(smem + warp * 16384);
-        const int d0 = lane * 4;
-        float4 g = *reinterpret_cast<const float4 *>(p.ln_g + d0);
-        float4 be = *reinterpret_cast<const float4 *>(p.ln_b + d0);
-        g.x *= p.alpha; g.y *= p.alpha; g.z *= p.alpha; g.w *= p.alpha;          // fold the exp2 pre-scale into the affine
-        be.x *= p.alpha; be.y *= p.alpha; be.z *= p.alpha; be.w *= p.alpha;
+        // ---- K parts -> Kq images: K = LN(Gk1[i] + Gk2[j]) * alpha in fp16, internal slot order  (model.py:69-82).
+        // Warp w holds TMEM lanes 32w..32w+31 = the 16 frames of windows 2w and 2w+1.  Two rounds; in each, every warp
+        // stages ONE of its windows (16 x 256 fp32 frame projections, centred) in shared memory (the operand stages are
+        // idle now), then the 128 epilogue threads build the four staged windows one after the other with
+        // THREAD == TUPLE SLOT: the LayerNorm statistics are thread-local (no shuffles), the frame rows are read as
+        // broadcast / 2-way LDS.128, the 32 KB operand image is assembled in shared memory in its final swizzled
+        // layout and leaves with one bulk store.
+        uint8_t *img = smem;                                                   // 32 KB
+        float *stg = reinterpret_cast<float *>(smem + 32768);                 // [4 windows][16 frames][260]
+        float *gs = reinterpret_cast<float *>(smem + 32768 + 4 * PROJ_STG);   // gamma*alpha [128] | beta*alpha [128]
+        const int tid = warp * 32 + lane;
+        gs[tid] = __ldg(p.ln_g + tid) * p.alpha;
+        gs[128 + tid] = __ldg(p.ln_b + tid) * p.alpha;
         // LayerNorm mean by linearity: mean(A_i + B_j) = mean(A_i) + mean(B_j), and every lane holds one whole frame
-        // row in its registers while staging -- so the rows are stored CENTRED and a tuple needs one reduction only.
-        const bool has_tb = p.table != nullptr;      // null: the table came in through the one-hot K columns
-        const float *tb = has_tb ? p.table + (int64_t)(lane & 15) * p.table_ld : nullptr;
-        float sumA = has_tb ? __ldg(p.table_sums + (lane & 15) * 2) : 0.f, sumB = has_tb ? __ldg(p.table_sums + (lane & 15) * 2 + 1) : 0.f;
+        // row in its TMEM lane -- so the rows are stored CENTRED and a tuple only needs the sum of squares.
+        float sumA = 0.f, sumB = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
           uint32_t v[32];
@@ -139,63 +144,71 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
           if (c0 < 128) sumA += (t0 + t1) + (t2 + t3); else sumB += (t0 + t1) + (t2 + t3);
         }
         const float mA = sumA * (1.0f / 128.0f), mB = sumB * (1.0f / 128.0f);
-        for (int wi = 0; wi < 2; ++wi) {
-          const int64_t win = (int64_t)mt * 8 + warp * 2 + wi;
-          __syncwarp();
+        const int fi = c_qslots[2 * tid], fj = c_qslots[2 * tid + 1];
+        const bool live = fi >= 0;                                            // pad slots are zero rows
+        uint8_t *irow = img + (tid >> 3) * 1024 + (tid & 7) * 128;
+        const bool run = p.alpha > 0.f;                                       // alpha < 0: timing-only, skip the tuple build
+        for (int rd = 0; rd < 2; ++rd) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + c0, v);
-            float4 tv[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tv[j] = has_tb ? __ldg(reinterpret_cast<const float4 *>(tb + c0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
-            if ((lane >> 4) == wi) {
+            if ((lane >> 4) == rd) {
               const float m = c0 < 128 ? mA : mB;
-              float *dst = ws + (lane & 15) * 256 + c0;
+              float *dst = stg + warp * (PROJ_STG / 4) + (lane & 15) * 260 + c0;
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(v[4 * j]) + tv[j].x - m, __uint_as_float(v[4 * j + 1]) + tv[j].y - m,
-                                                                       __uint_as_float(v[4 * j + 2]) + tv[j].z - m, __uint_as_float(v[4 * j + 3]) + tv[j].w - m);
+                *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(v[4 * j]) - m, __uint_as_float(v[4 * j + 1]) - m,
+                                                                       __uint_as_float(v[4 * j + 2]) - m, __uint_as_float(v[4 * j + 3]) - m);
             }
           }
-          __syncwarp();
-          if (win * 16 < p.M && p.alpha > 0.f) {
-            uint8_t *out = reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768;
-            // NU tuple rows per iteration so that their variance reductions (5 dependent shuffles each) interleave
-            constexpr int NU = 8;
+          named_bar_sync(1, 128);
 #pragma unroll 1
-            for (int s4 = 0; s4 < 128; s4 += NU) {
-              float4 k[NU];
-              float q[NU];
-              bool ok[NU];
+          for (int wn = 0; wn < 4; ++wn) {
+            const int64_t win = (int64_t)mt * 8 + wn * 2 + rd;
+            if (win * 16 >= p.M || !run) continue;                            // uniform over the CTA
+            const float4 *A = reinterpret_cast<const float4 *>(stg + wn * (PROJ_STG / 4) + (live ? fi : 0) * 260);
+            const float4 *B = reinterpret_cast<const float4 *>(stg + wn * (PROJ_STG / 4) + (live ? fj : 0) * 260 + 128);
+            uint64_t x[64];                                                   // the tuple row, zero-mean, as fp32 pairs
+            uint64_t q0 = 0ull, q1 = 0ull;
 #pragma unroll
-              for (int u = 0; u < NU; ++u) {
-                const int fi = c_qslots[2 * (s4 + u)], fj = c_qslots[2 * (s4 + u) + 1];
-                ok[u] = fi >= 0;
-                const float4 a = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fi : 0) * 256 + d0);
-                const float4 b = *reinterpret_cast<const float4 *>(ws + (ok[u] ? fj : 0) * 256 + 128 + d0);
-                k[u] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);          // already zero-mean
-                q[u] = k[u].x * k[u].x + k[u].y * k[u].y + k[u].z * k[u].z + k[u].w * k[u].w;
+            for (int c = 0; c < 32; ++c) {
+              const float4 a = A[c], b = B[c];
+              x[2 * c] = add2(pack2(a.x, a.y), pack2(b.x, b.y));
+              x[2 * c + 1] = add2(pack2(a.z, a.w), pack2(b.z, b.w));
+              q0 = fma2(x[2 * c], x[2 * c], q0);
+              q1 = fma2(x[2 * c + 1], x[2 * c + 1], q1);
+            }
+            float ql, qh;
+            unpack2(add2(q0, q1), ql, qh);
+            const float rstd = live ? rsqrtf((ql + qh) * (1.0f / 128.0f) + 1e-5f) : 0.f;
+            const uint64_t rr = pack2(rstd, rstd);
+            if (tid == 0) bulk_wait_read_all();                               // the previous image has left shared memory
+            named_bar_sync(2, 128);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              uint32_t h[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 g2 = *reinterpret_cast<const float2 *>(gs + c * 8 + 2 * k);
+                const float2 e2 = *reinterpret_cast<const float2 *>(gs + 128 + c * 8 + 2 * k);
+                float lo, hi;
+                unpack2(fma2(mul2(x[c * 4 + k], rr), pack2(g2.x, g2.y), pack2(e2.x, e2.y)), lo, hi);
+                const __half2 hh = __floats2half2_rn(lo, hi);
+                h[k] = live ? *reinterpret_cast<const uint32_t *>(&hh) : 0u;
               }
-#pragma unroll
-              for (int o = 16; o; o >>= 1) {
-#pragma unroll
-                for (int u = 0; u < NU; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
-              }
-#pragma unroll
-              for (int u = 0; u < NU; ++u) {
-                const float rstd = rsqrtf(q[u] * (1.0f / 128.0f) + 1e-5f);
-                __half2 h0 = __floats2half2_rn(fmaf(k[u].x * rstd, g.x, be.x), fmaf(k[u].y * rstd, g.y, be.y));
-                __half2 h1 = __floats2half2_rn(fmaf(k[u].z * rstd, g.z, be.z), fmaf(k[u].w * rstd, g.w, be.w));
-                uint2 packed;
-                packed.x = ok[u] ? *reinterpret_cast<uint32_t *>(&h0) : 0u;
-                packed.y = ok[u] ? *reinterpret_cast<uint32_t *>(&h1) : 0u;
-                *reinterpret_cast<uint2 *>(out + (d0 >> 6) * 16384 + sw128_offset(s4 + u, d0 & 63)) = packed;
-              }
+              *reinterpret_cast<uint4 *>(irow + (c >> 3) * 16384 + (((c & 7) ^ (tid & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3, 128);
+            if (tid == 0) {
+              bulk_s2g(reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768, img, 32768);
+              bulk_commit();
             }
           }
         }
+        if (tid == 0) bulk_wait_all();
       } else {
         // ---- V parts: fp32 [M][256] (bias and positional-encoding table folded in), read by the attention epilogues
 #pragma unroll 1
@@ -378,7 +391,8 @@ __global__ void k_pad_bias(const float *__restrict__ b, int N, float *__restrict
 }
 
 template <int BN, int OUT, int NST = 2> int launch_gemm(arx_handle *h, const GemmParams &p, int n_tiles, cudaStream_t st) {
-  constexpr uint32_t smem = NST * (A_SUB + BN * 128) + (2 * NST + 1) * 8 + 16 + 1024;
+  constexpr uint32_t body = (OUT == OUT_PROJ16 && PROJ_EPI > NST * (A_SUB + BN * 128)) ? PROJ_EPI : NST * (A_SUB + BN * 128);
+  constexpr uint32_t smem = body + (2 * NST + 1) * 8 + 16 + 1024;
   auto kern = k_gemm_tc<BN, OUT, NST>;
   ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((p.M + 127) / 128), (unsigned)n_tiles);
@@ -447,6 +461,7 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
                          cudaStream_t st) {
   if (L.BN != 256 || L.n_tiles != 2) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: needs a 512-column projection");
   (void)table_sums;
+  if (table) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: the positional table must come in through the one-hot K columns");
   static bool slots_set = false;
   if (!slots_set) {
     ARX_CUDA(h, cudaMemcpyToSymbol(c_qslots, slots_host, 256 * sizeof(int)));

@@ -98,7 +98,7 @@ struct arx_handle {
   int64_t prof_chunks = 0;
   int last_path = 0;
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
-  int attn_stagger = 1000;   // clocks softmax group 1 starts behind group 0 in k_attn_tc3 (debug key 3)
+  int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
   bool pdl = false;     // programmatic dependent launch for the arx_score kernel chain (debug key 2; measured: no gain, off by default)
   int tc_variant = 0;   // debug: bit 0 selects the K-major P layout
   std::string err;
@@ -157,7 +157,7 @@ int arx_tc_support_build(arx_handle *h, ArxTransformer &tr, const float *G, int 
 int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st);
 bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, cudaStream_t st);
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, cudaStream_t st);
 
 bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st);
@@ -213,7 +213,14 @@ int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a
 int arx_tc_build_wp_ext(arx_handle *h, const float *wp, const float *table, float *out, int N, int F, cudaStream_t st);
 
 int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, int g_ld, int g_voff, cudaStream_t st);
+                             float *partial, int g_ld, int g_voff, bool g_chunked, cudaStream_t st);
+// ---- persistent GEMM + tuple images (arx_gemm_p.cu)
+bool arx_tcp_supported(const ArxTcLinear &L);
+int arx_tcp_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,
+                       cudaStream_t st);
+int arx_tcp_linear_chunked(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *gc, cudaStream_t st);
+int arx_tuple_img(arx_handle *h, const ArxTransformer &tr, const float *gc, int n_chunks, int64_t n_win, __half *kq_img, float alpha,
+                  cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

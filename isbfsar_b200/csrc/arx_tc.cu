@@ -907,7 +907,7 @@ int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t
 }
 
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, cudaStream_t st) {
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, cudaStream_t st) {
   AttnParams p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.G = G; p.Vq = Vq; p.partial = partial;
   p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = g_ld; p.voff = g_voff;
@@ -917,7 +917,7 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
   if (mode0 && arx_tc_slot_order(h, tr)) {
     // third-generation kernel by default; variant bit 7 (128) selects the second generation
     int rc = (variant & 128) ? arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st)
-                             : arx_tc3_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st);
+                             : arx_tc3_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, g_chunked, st);
     if (rc) return rc;
     ARX_CUDA(h, arx_launch_pdl(k_finish_tc, dim3((unsigned)((n_win + 127) / 128)), dim3(128), 0, st, h->pdl, (const float *)partial, logits, chosen,
                                (int64_t)n_win, way, tr.N));

@@ -37,7 +37,7 @@ struct Attn3Params {
   float *partial;
   int n_win, way, ldg, voff;
   long long *trace;
-  int stagger, token;
+  int stagger, token, gchunk;
 };
 #define ARX_TRACE_TILES 64
 #define TRACE3(role, tile, k) do { if (p.trace && blockIdx.x == 0 && (tile) < ARX_TRACE_TILES) p.trace[(((role) * ARX_TRACE_TILES) + (tile)) * 8 + (k)] = clock64(); } while (0)
@@ -190,7 +190,11 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
               mma_commit(&bars[B_P_EMPTY + w]);
             }
             // barriers of an absent second window keep their phase in step
-            if (nw == 1) { mbar_arrive(&bars[B_O_FULL + 1]); mbar_arrive(&bars[B_P_EMPTY + 1]); }
+            if (nw == 1) {          // sequenced like a real tile (see the parity note in the softmax branch)
+              mbar_wait(&bars[B_O_EMPTY + 1], (k & 1) ^ 1);
+              mbar_arrive(&bars[B_O_FULL + 1]);
+              mbar_arrive(&bars[B_P_EMPTY + 1]);
+            }
             mma_commit(&bars[B_EMPTY_VC + st]);
           }
         }
@@ -218,6 +222,9 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
         }
         if (g >= nw) {              // single-window tail group: slot 1 has no tile, but its barriers must keep their phase
           mbar_arrive(&bars[B_S_EMPTY]);
+          // take the MUFU token in turn like a real tile: an mbarrier parity wait cannot tell phase k from k+2, so
+          // no barrier may ever run two phases ahead of its waiter
+          if (p.token) mbar_wait(&bars[B_XU + 0], k & 1);
           mbar_arrive(&bars[B_XU + 1]);
           mbar_arrive(&bars[B_P_FULL + 1]);
           continue;
@@ -283,18 +290,30 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
     int gi = 0, c = 0, nw = my_groups ? group_nw(0) : 0, g = blockIdx.x;
     for (int k = 0; k < my_groups * p.way; ++k) {
       if (c == 0) {
-        const float *g0 = p.G + (size_t)(g * 2) * 16 * p.ldg + p.voff + d;
+        // per-frame V projections of the group's windows (v bias / positional table already inside).  Row-major
+        // [frame][ldg] or the chunked layout of arx_gemm_p.cu (32-column chunks of 128 rows, 16-byte groups swizzled)
+        auto load_ab = [&](int win, float (&a)[16], uint64_t (&bb)[8]) {
+          if (p.gchunk) {
+            const int r0 = (win & 7) * 16;
+            const float *ca = p.G + ((size_t)(win >> 3) * 16 + ((p.voff + d) >> 5)) * 4096;
+            const float *cb = ca + 4 * 4096;                                   // second V part: 128 columns = 4 chunks on
+            const int qd = (d & 31) >> 2, e = d & 3;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a0[i] = __ldg(g0 + (size_t)i * p.ldg);
+            for (int i = 0; i < 16; ++i) a[i] = __ldg(ca + (r0 + i) * 32 + (((qd ^ (i & 7)) << 2) | e));
 #pragma unroll
-        for (int m = 0; m < 8; ++m) bb0[m] = pack2(__ldg(g0 + (size_t)(2 * m) * p.ldg + DD), __ldg(g0 + (size_t)(2 * m + 1) * p.ldg + DD));
-        if (nw > 1) {
-          const float *g1 = g0 + (size_t)16 * p.ldg;
+            for (int m = 0; m < 8; ++m)
+              bb[m] = pack2(__ldg(cb + (r0 + 2 * m) * 32 + (((qd ^ ((2 * m) & 7)) << 2) | e)),
+                            __ldg(cb + (r0 + 2 * m + 1) * 32 + (((qd ^ ((2 * m + 1) & 7)) << 2) | e)));
+          } else {
+            const float *g0 = p.G + (size_t)win * 16 * p.ldg + p.voff + d;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a1[i] = __ldg(g1 + (size_t)i * p.ldg);
+            for (int i = 0; i < 16; ++i) a[i] = __ldg(g0 + (size_t)i * p.ldg);
 #pragma unroll
-          for (int m = 0; m < 8; ++m) bb1[m] = pack2(__ldg(g1 + (size_t)(2 * m) * p.ldg + DD), __ldg(g1 + (size_t)(2 * m + 1) * p.ldg + DD));
-        }
+            for (int m = 0; m < 8; ++m) bb[m] = pack2(__ldg(g0 + (size_t)(2 * m) * p.ldg + DD), __ldg(g0 + (size_t)(2 * m + 1) * p.ldg + DD));
+          }
+        };
+        load_ab(g * 2, a0, bb0);
+        if (nw > 1) load_ab(g * 2 + 1, a1, bb1);
       }
       // one tile: window slot w (compile-time, so a/bb stay in registers) of class c
       auto tile = [&](auto wc, const float (&a)[16], const uint64_t (&bb)[8]) {
@@ -337,10 +356,11 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
 }  // namespace
 
 int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, int g_ld, int g_voff, cudaStream_t st) {
+                             float *partial, int g_ld, int g_voff, bool g_chunked, cudaStream_t st) {
   Attn3Params p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img_bf; p.G = G; p.partial = partial;
   p.n_win = (int)n_win; p.way = way; p.ldg = g_ld; p.voff = g_voff; p.trace = h->trace_buf;
+  p.gchunk = g_chunked ? 1 : 0;
   p.token = h->attn_stagger < 0;
   p.stagger = h->attn_stagger < 0 ? 0 : h->attn_stagger;
   const int groups = (int)((n_win + 1) / 2);
