@@ -295,6 +295,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     ARX_CUDA(h, cudaMemcpyAsync(g.data(), tr.ln_g, D * sizeof(float), cudaMemcpyDeviceToHost, st));
     ARX_CUDA(h, cudaMemcpyAsync(b.data(), tr.ln_b, D * sizeof(float), cudaMemcpyDeviceToHost, st));
     ARX_CUDA(h, cudaStreamSynchronize(st));
+    if (D == 128) { memcpy(tr.ln_host, g.data(), 128 * sizeof(float)); memcpy(tr.ln_host + 128, b.data(), 128 * sizeof(float)); }
     double gm = 0, bn = 0;
     for (int d = 0; d < D; ++d) { gm = std::max(gm, (double)fabsf(g[d])); bn += (double)b[d] * b[d]; }
     double r = gm * sqrt((double)D) + sqrt(bn);

@@ -24,7 +24,6 @@ using namespace ptx;
 
 constexpr uint32_t A_SUB = 128 * 128;       // 128 rows x 64 fp16
 constexpr int P_THREADS = 192;
-constexpr uint32_t P_STG = 4 * 4096;        // per-warp 4 KB epilogue staging
 enum { POUT_IMG16 = 0, POUT_F32C = 1 };
 
 struct GemmPParams {
@@ -39,12 +38,15 @@ struct GemmPParams {
   float *gc;               // POUT_F32C: chunked projections, n_tiles*BN/32 chunks per row tile
 };
 
-template <int BN, int OUT>
+// NSTG = 4 KB staging blocks per epilogue warp: a bulk store takes ~1000 clocks to release its source, so a warp
+// needs several blocks in flight unless the layer is HBM-bound anyway
+template <int BN, int OUT, int NSTG>
 __global__ void __launch_bounds__(P_THREADS, 1) k_gemm_p(const GemmPParams p) {
   constexpr uint32_t B_SUB = BN * 128;
+  constexpr uint32_t P_STG = 4 * NSTG * 4096;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t off_a = p.nk * B_SUB, off_stg = off_a + p.nsta * A_SUB, off_bar = off_stg + P_STG;
+  const uint32_t off_a = p.nk * B_SUB, off_stg = off_a + p.nsta * A_SUB, off_bias = off_stg + P_STG, off_bar = off_bias + BN * 4;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + off_bar);   // b_full, a_full[nsta], a_empty[nsta], acc_full[2], acc_empty[2]
   uint64_t *b_full = bars, *a_full = bars + 1, *a_empty = bars + 1 + p.nsta, *acc_full = bars + 1 + 2 * p.nsta, *acc_empty = acc_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
@@ -106,9 +108,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_gemm_p(const GemmPParams p) {
     // epilogue: thread == row of the tile == TMEM lane; each warp owns 32 rows and a 4 KB staging block
     const int r = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    uint8_t *stg = smem + off_stg + warp * 4096;
-    uint8_t *srow = stg + lane * 128;
-    int t = 0;
+    uint8_t *stg0 = smem + off_stg + warp * (NSTG * 4096);
+    float *sbias = reinterpret_cast<float *>(smem + off_bias);      // this column tile's bias: the L1 is tiny beside 220 KB of shared memory
+    for (int i = threadIdx.x; i < BN; i += 128) sbias[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.f;
+    named_bar_sync(1, 128);
+    int t = 0, sb = 0;                                              // sb: staging block in use
     for (int mt = m0; mt < p.m_tiles; mt += m_stride, ++t) {
       const int buf = t & 1;
       mbar_wait(&acc_full[buf], (t >> 1) & 1);
@@ -135,11 +139,13 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_gemm_p(const GemmPParams p) {
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + buf * 256 + c0, v);
-        const bool first = OUT == POUT_F32C || (c0 & 32) == 0;       // first chunk of a staging block: the previous
-        if (first) {                                                  // bulk store must have left the staging memory
-          if (lane == 0) bulk_wait_read_all();
+        const bool first = OUT == POUT_F32C || (c0 & 32) == 0;       // first chunk of a staging block: the bulk store
+        if (first) {                                                  // issued NSTG blocks ago must have left it
+          if (lane == 0) bulk_wait_read<NSTG - 1>();
           __syncwarp();
         }
+        uint8_t *stg = stg0 + sb * 4096;
+        uint8_t *srow = stg + lane * 128;
         tmem_ld_wait();
         if (c0 + 32 >= BN) {                                          // accumulator drained: the MMA warp may reuse it
           tc_fence_before();
@@ -157,11 +163,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_gemm_p(const GemmPParams p) {
             bulk_s2g(dst, stg, 4096);
             bulk_commit();
           }
+          sb = (sb + 1) % NSTG;
         } else {
           float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float tv = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+            float tv = __uint_as_float(v[j]) + sbias[c0 + j];
             if (p.act == ARX_ACT_RELU) tv = fmaxf(tv, 0.f);
             x[j] = tv;
           }
@@ -183,6 +190,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) k_gemm_p(const GemmPParams p) {
               bulk_s2g(dst, stg, 4096);
               bulk_commit();
             }
+            sb = (sb + 1) % NSTG;
           }
         }
       }
@@ -199,50 +207,26 @@ constexpr int TI_STRIDE = 260;        // padded frame row (floats): 16 distinct 
 
 __constant__ int c_pslots[256];       // frame pair of every internal slot, -1 = pad
 
-__global__ void __launch_bounds__(128, 3) k_tuple_img(const float *__restrict__ gc, int n_chunks, const float *__restrict__ ln_g,
-                                                      const float *__restrict__ ln_b, float alpha, __half *__restrict__ kq_img, int n_win) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  uint8_t *img = smem;                                                   // 32 KB, final swizzled layout
-  float *stg = reinterpret_cast<float *>(smem + 32768);                 // [16 frames][260]: K part 1 | K part 2, centred
-  float *gs = stg + 16 * TI_STRIDE;                                     // gamma*alpha [128] | beta*alpha [128]
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int win = blockIdx.x;
-  gs[tid] = __ldg(ln_g + tid) * alpha;
-  gs[128 + tid] = __ldg(ln_b + tid) * alpha;
-  {
-    // stage the window's 16 x 256 K projections: 1024 float4, 8 per thread; a warp covers one (frame, part) per
-    // pass, so the LayerNorm mean by linearity (mean(A_i + B_j) = mean(A_i) + mean(B_j)) is one warp reduction
-    const float4 *src = reinterpret_cast<const float4 *>(gc) + (size_t)(win >> 3) * n_chunks * 128 * 8;
-    const int r0 = (win & 7) * 16;
-    float4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int idx = k * 128 + tid;                // = frame * 64 + quad,  quad = 16-byte group of the 256 K columns
-      const int fr = idx >> 6, quad = idx & 63;
-      const int row = r0 + fr;
-      v[k] = __ldg(src + ((size_t)(quad >> 3) * 128 + row) * 8 + ((quad & 7) ^ (row & 7)));
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float s = (v[k].x + v[k].y) + (v[k].z + v[k].w);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float m = s * (1.0f / 128.0f);
-      const int idx = k * 128 + tid;
-      const int fr = idx >> 6, quad = idx & 63;
-      *reinterpret_cast<float4 *>(stg + fr * TI_STRIDE + quad * 4) = make_float4(v[k].x - m, v[k].y - m, v[k].z - m, v[k].w - m);
-    }
-  }
-  __syncthreads();
-  const int fi = c_pslots[2 * tid], fj = c_pslots[2 * tid + 1];
-  const bool live = fi >= 0;
-  const float4 *A = reinterpret_cast<const float4 *>(stg + (live ? fi : 0) * TI_STRIDE);
-  const float4 *B = reinterpret_cast<const float4 *>(stg + (live ? fj : 0) * TI_STRIDE + 128);
-  uint64_t x[64];
+struct TupleParams {
+  float gs[256];            // gamma*alpha [128] | beta*alpha [128]: read as constant-bank operands, not through the LSU
+  const float *gc;
+  __half *kq_img;
+  int n_chunks, n_win;
+};
+
+// 256 threads: thread (slot s = tid & 127, HALF = tid >> 7) owns 64 of the 128 dimensions of tuple row s -- 16 warps
+// per SM at <= 128 registers instead of 8 at 255.  HALF is warp-uniform and a template parameter of the body, so the
+// LayerNorm affine stays a compile-time constant-bank operand; the two halves of a row exchange their sums of
+// squares through shared memory under a barrier the loop needs anyway.
+template <int HALF>
+__device__ __forceinline__ void tuple_body(const TupleParams &p, const float *stg, float *sq, uint8_t *img0, int fi, int fj, bool live, int s,
+                                           int it, int win) {
+  const float4 *A = reinterpret_cast<const float4 *>(stg + (live ? fi : 0) * TI_STRIDE + HALF * 64);
+  const float4 *B = reinterpret_cast<const float4 *>(stg + (live ? fj : 0) * TI_STRIDE + 128 + HALF * 64);
+  uint64_t x[32];
   uint64_t q0 = 0ull, q1 = 0ull;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
+  for (int c = 0; c < 16; ++c) {
     const float4 a = A[c], b = B[c];
     x[2 * c] = add2(pack2(a.x, a.y), pack2(b.x, b.y));
     x[2 * c + 1] = add2(pack2(a.z, a.w), pack2(b.z, b.w));
@@ -251,42 +235,87 @@ __global__ void __launch_bounds__(128, 3) k_tuple_img(const float *__restrict__ 
   }
   float ql, qh;
   unpack2(add2(q0, q1), ql, qh);
-  const float rstd = live ? rsqrtf((ql + qh) * (1.0f / 128.0f) + 1e-5f) : 0.f;
+  sq[HALF * 128 + s] = ql + qh;
+  if (threadIdx.x == 0) bulk_wait_read<1>();        // the store that used this image buffer two windows ago has left it
+  named_bar_sync(1, 256);                           // ... everybody is done with the staged rows, partial sums visible
+  const float rstd = live ? rsqrtf((sq[s] + sq[128 + s]) * (1.0f / 128.0f) + 1e-5f) : 0.f;
   const uint64_t rr = pack2(rstd, rstd);
-  uint8_t *irow = img + (tid >> 3) * 1024 + (tid & 7) * 128;
+  uint8_t *img = img0 + (it & 1) * 32768;
+  uint8_t *irow = img + HALF * 16384 + (s >> 3) * 1024 + (s & 7) * 128;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int c = 0; c < 8; ++c) {
     uint32_t h[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 g2 = *reinterpret_cast<const float2 *>(gs + c * 8 + 2 * k);
-      const float2 e2 = *reinterpret_cast<const float2 *>(gs + 128 + c * 8 + 2 * k);
+      constexpr int D0 = HALF * 64;
       float lo, hi;
-      unpack2(fma2(mul2(x[c * 4 + k], rr), pack2(g2.x, g2.y), pack2(e2.x, e2.y)), lo, hi);
-      const __half2 hh = __floats2half2_rn(lo, hi);
+      unpack2(mul2(x[c * 4 + k], rr), lo, hi);
+      const __half2 hh = __floats2half2_rn(fmaf(lo, p.gs[D0 + c * 8 + 2 * k], p.gs[128 + D0 + c * 8 + 2 * k]),
+                                           fmaf(hi, p.gs[D0 + c * 8 + 2 * k + 1], p.gs[128 + D0 + c * 8 + 2 * k + 1]));
       h[k] = live ? *reinterpret_cast<const uint32_t *>(&hh) : 0u;
     }
-    *reinterpret_cast<uint4 *>(irow + (c >> 3) * 16384 + (((c & 7) ^ (tid & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(irow + ((c ^ (s & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
   }
   fence_proxy_async_smem();
-  __syncthreads();
-  if (tid == 0) {
-    bulk_s2g(reinterpret_cast<uint8_t *>(kq_img) + (size_t)win * 32768, img, 32768);
+  named_bar_sync(1, 256);                           // (named: the two HALF bodies are different code paths)
+  if (threadIdx.x == 0) {
+    bulk_s2g(reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768, img, 32768);
     bulk_commit();
-    bulk_wait_all();
   }
-  (void)n_win; (void)lane;
 }
 
-template <int BN, int OUT> int launch_p(arx_handle *h, GemmPParams &p, cudaStream_t st) {
-  const uint32_t fixed = p.nk * BN * 128 + P_STG + 256 + 1024;
+__global__ void __launch_bounds__(256, 2) k_tuple_img(const __grid_constant__ TupleParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t *img0 = smem;                                                  // 2 x 32 KB, final swizzled layout
+  float *stg = reinterpret_cast<float *>(smem + 65536);                 // [16 frames][260]: K part 1 | K part 2, centred
+  float *sq = stg + 16 * TI_STRIDE;                                     // [2 halves][128 slots] partial sums of squares
+  const int tid = threadIdx.x, s = tid & 127;
+  const int fi = c_pslots[2 * s], fj = c_pslots[2 * s + 1];
+  const bool live = fi >= 0;
+  // the window's 16 x 256 K projections: 1024 float4, 4 per thread; a warp covers one (frame, part) per pass, so
+  // the LayerNorm mean by linearity (mean(A_i + B_j) = mean(A_i) + mean(B_j)) is one warp reduction.  The loads
+  // of the NEXT window are issued before this window's arithmetic (persistent CTA, software pipeline).
+  float4 v[4];
+  auto fetch = [&](int win) {
+    const float4 *src = reinterpret_cast<const float4 *>(p.gc) + (size_t)(win >> 3) * p.n_chunks * 128 * 8;
+    const int r0 = (win & 7) * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = k * 256 + tid;                // = frame * 64 + quad,  quad = 16-byte group of the 256 K columns
+      const int row = r0 + (idx >> 6), quad = idx & 63;
+      v[k] = __ldg(src + ((size_t)(quad >> 3) * 128 + row) * 8 + ((quad & 7) ^ (row & 7)));
+    }
+  };
+  int win = blockIdx.x;
+  if (win < p.n_win) fetch(win);
+  for (int it = 0; win < p.n_win; win += gridDim.x, ++it) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float sum = (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float m = sum * (1.0f / 128.0f);
+      const int idx = k * 256 + tid;
+      *reinterpret_cast<float4 *>(stg + (idx >> 6) * TI_STRIDE + (idx & 63) * 4) = make_float4(v[k].x - m, v[k].y - m, v[k].z - m, v[k].w - m);
+    }
+    __syncthreads();
+    if (win + (int)gridDim.x < p.n_win) fetch(win + gridDim.x);
+    if (tid < 128) tuple_body<0>(p, stg, sq, img0, fi, fj, live, s, it, win);
+    else tuple_body<1>(p, stg, sq, img0, fi, fj, live, s, it, win);
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
+template <int BN, int OUT, int NSTG> int launch_p(arx_handle *h, GemmPParams &p, cudaStream_t st) {
+  const uint32_t fixed = p.nk * BN * 128 + 4 * NSTG * 4096 + BN * 4 + 256 + 1024;
   const uint32_t cap = 232448;
   int nsta = (int)((cap - fixed) / A_SUB);
   if (nsta > 8) nsta = 8;
   if (nsta < 2) return arx_fail(h, ARX_ERR_INVALID, "gemm_p: weights of this layer do not fit in shared memory (nk=%d BN=%d)", p.nk, BN);
   p.nsta = nsta;
   const uint32_t smem = fixed + nsta * A_SUB;
-  auto kern = k_gemm_p<BN, OUT>;
+  auto kern = k_gemm_p<BN, OUT, NSTG>;
   ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (h->sm_count / p.n_tiles) * p.n_tiles;
   if (grid > p.m_tiles * p.n_tiles) grid = p.m_tiles * p.n_tiles;
@@ -297,7 +326,7 @@ template <int BN, int OUT> int launch_p(arx_handle *h, GemmPParams &p, cudaStrea
 
 }  // namespace
 
-bool arx_tcp_supported(const ArxTcLinear &L) { return (L.BN == 256 || L.BN == 192) && (size_t)L.nk * L.BN * 128 + 2 * A_SUB + P_STG + 2048 <= 232448; }
+bool arx_tcp_supported(const ArxTcLinear &L) { return (L.BN == 256 || L.BN == 192) && (size_t)L.nk * L.BN * 128 + 2 * A_SUB + 4 * 4096 + 4096 <= 232448; }
 
 // act(A.W^T + b) -> fp16 activation image with c_nk K-sub-tiles per row tile (persistent kernel)
 int arx_tcp_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,
@@ -305,8 +334,8 @@ int arx_tcp_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img,
   GemmPParams p{};
   p.a_img = a_img; p.w_img = L.w_img; p.bias = L.bias; p.nk = L.nk; p.a_nk = L.nk; p.m_tiles = (int)((M + 127) / 128); p.n_tiles = L.n_tiles;
   p.act = act; p.c_img = c_img; p.c_nk = c_nk; p.onehot_sub = onehot_sub;
-  if (L.BN == 192) return launch_p<192, POUT_IMG16>(h, p, st);
-  if (L.BN == 256) return launch_p<256, POUT_IMG16>(h, p, st);
+  if (L.BN == 192) return launch_p<192, POUT_IMG16, 4>(h, p, st);
+  if (L.BN == 256) return launch_p<256, POUT_IMG16, 4>(h, p, st);
   return arx_fail(h, ARX_ERR_INVALID, "tcp_linear_img: unsupported BN %d", L.BN);
 }
 
@@ -315,7 +344,7 @@ int arx_tcp_linear_chunked(arx_handle *h, const ArxTcLinear &L, const __half *a_
   GemmPParams p{};
   p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = a_nk; p.m_tiles = (int)((M + 127) / 128); p.n_tiles = L.n_tiles;
   p.act = ARX_ACT_NONE; p.gc = gc; p.onehot_sub = -1;
-  if (L.BN == 256) return launch_p<256, POUT_F32C>(h, p, st);
+  if (L.BN == 256) return launch_p<256, POUT_F32C, 1>(h, p, st);
   return arx_fail(h, ARX_ERR_INVALID, "tcp_linear_chunked: unsupported BN %d", L.BN);
 }
 
@@ -329,9 +358,13 @@ int arx_tuple_img(arx_handle *h, const ArxTransformer &tr, const float *gc, int 
     ARX_CUDA(h, cudaMemcpyToSymbol(c_pslots, slots, sizeof(slots)));
     slots_set = true;
   }
-  const uint32_t smem = 32768 + 16 * TI_STRIDE * 4 + 1024 + 128;
+  const uint32_t smem = 65536 + 16 * TI_STRIDE * 4 + 1024 + 128;
   ARX_CUDA(h, cudaFuncSetAttribute(k_tuple_img, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tuple_img<<<(unsigned)n_win, 128, smem, st>>>(gc, n_chunks, tr.ln_g, tr.ln_b, alpha, kq_img, (int)n_win);
+  const int64_t grid = n_win < 2 * h->sm_count ? n_win : 2 * h->sm_count;
+  TupleParams p{};
+  for (int d = 0; d < 128; ++d) { p.gs[d] = tr.ln_host[d] * alpha; p.gs[128 + d] = tr.ln_host[128 + d] * alpha; }
+  p.gc = gc; p.kq_img = kq_img; p.n_chunks = n_chunks; p.n_win = (int)n_win;
+  k_tuple_img<<<(unsigned)grid, 256, smem, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }

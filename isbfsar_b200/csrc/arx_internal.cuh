@@ -27,6 +27,7 @@ struct ArxTransformer {
   float *wp_ext = nullptr;  // (2cD, F+32): wp | hi(table)^T | lo(table)^T -- the table enters the GEMM through one-hot K columns (T == 16)
   bool table_in_gemm = false;
   float *ln_g = nullptr, *ln_b = nullptr;
+  float ln_host[256] = {};  // host copy [gamma(128) | beta(128)] when D == 128: kernel-parameter operands of k_tuple_img
   int32_t *tuples = nullptr; // (N,c) int32, built on device
   int32_t *q_slots = nullptr; // (128,2) internal padded-triangular order of the query tuples (T=16 pairs), -1 = pad
   // support operands, fp32 generic path: (W,N,D) each
