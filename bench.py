@@ -96,7 +96,7 @@ def ncu_traffic_bytes():
     p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
     try:
         for d in json.load(open(p)):
-            if "k_attn_tc2" in d["Kernel Name"]:
+            if "k_attn_tc" in d["Kernel Name"]:
                 scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
                 rd = float(d["dram__bytes_read.sum"]) * scale[d["units"]["dram__bytes_read.sum"]]
                 wr = float(d["dram__bytes_write.sum"]) * scale[d["units"]["dram__bytes_write.sum"]]

@@ -166,8 +166,16 @@ ARX_API int arx_decode_heatmaps(arx_handle *h, const float *logits_dev, int64_t 
 ARX_API int arx_profile_enable(arx_handle *h, int32_t on);
 ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset);
 
-/* Debug knobs for kernel bring-up and tests.  key 0: tcgen05 attention variant (bit 0 = K-major
- * layout of the P operand instead of MN-major). */
+/* Debug knobs for kernel bring-up and tests.
+ *  key 0: kernel-variant bit mask -- 1 K-major P operand (first-generation attention), 2 fp32 open-set head,
+ *         4 fp32 CUDA-core linear layers, 8 first-generation attention kernel, 16 unfused projection (row-major
+ *         projections + k_prep_k_img), 32 first-generation head pass, 64 timing only: skip the tuple build,
+ *         128 second-generation attention kernel, 512 tuple build inside the projection GEMM epilogue,
+ *         1024 one-tile-per-CTA GEMMs for the frame MLP, 2048 head projection on the caller's stream.
+ *  key 1: (value != 0) arm a timeline trace of CTA 0 of the attention kernel.
+ *  key 2: programmatic dependent launch for the score kernel chain.
+ *  key 3: softmax-group scheduling of the attention kernel: < 0 the groups take turns on the MUFU phase
+ *         (default), >= 0 free-running with group 1 started this many clocks late. */
 ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
 /* key 1 (value != 0) arms a timeline trace of CTA 0 of the attention kernel; this reads it back:
  * host_out[3 roles][64 tiles][8 stamps] of SM clock values (bring-up tool). */

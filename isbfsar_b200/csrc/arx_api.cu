@@ -241,6 +241,9 @@ void arx_destroy(arx_handle *h) {
   }
   if (h->hs_h2d) { cudaStreamDestroy(h->hs_h2d); cudaStreamDestroy(h->hs_comp); cudaStreamDestroy(h->hs_d2h); }
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_aux_fork) cudaEventDestroy(h->ev_aux_fork);
+  if (h->ev_aux_done) cudaEventDestroy(h->ev_aux_done);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_support_done) cudaEventDestroy(h->ev_support_done);
   if (h->ev_score_done) cudaEventDestroy(h->ev_score_done);
@@ -655,6 +658,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   h->last_path = use_tc ? 2 : 1;
   if (st != h->hs_comp && h->hs_submitted > 0)      // the shared workspace may still be in use by streamed requests
     ARX_CUDA(h, cudaStreamWaitEvent(st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0));
+  bool aux_pending = false;
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
     const int64_t n = std::min(chunk, n_windows - b0);
     const float *FE;
@@ -687,7 +691,23 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         } else if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G,
                                               tr.table_in_gemm ? nullptr : tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
           return rc;
-        if (head2 && (rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows, w.uab, 32, tr.tcomp, h->T, st))) return rc;
+        if (head2) {
+          // only the head pass reads these 32 columns: run them on a second stream, beside projection + attention
+          const bool aux = (h->tc_variant & 2048) == 0 && !h->prof_on;
+          cudaStream_t us = st;
+          if (aux) {
+            if (!h->aux_stream) {
+              ARX_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+              ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
+              ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_done, cudaEventDisableTiming));
+            }
+            us = h->aux_stream;
+            ARX_CUDA(h, cudaEventRecord(h->ev_aux_fork, st));
+            ARX_CUDA(h, cudaStreamWaitEvent(us, h->ev_aux_fork, 0));
+          }
+          if ((rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows, w.uab, 32, tr.tcomp, h->T, us))) return rc;
+          if (aux) { ARX_CUDA(h, cudaEventRecord(h->ev_aux_done, us)); aux_pending = true; }
+        }
       } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, 2 * tr.c * h->D, tr.table_in_gemm ? nullptr : tr.bp, h->T, st)))
         return rc;
     } else {
@@ -714,6 +734,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
       if (disc && head2) {
+        if (aux_pending) { ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_aux_done, 0)); aux_pending = false; }
         if ((rc = arx_tc2_head_launch(h, tr, w.kq_img, w.uab, n, ch, w.y_img, h->tl_d1.nk, st))) return rc;
       } else if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
                                                                h->tl_d1.nk, g_ld, g_voff, st)))

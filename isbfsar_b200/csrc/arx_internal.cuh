@@ -67,6 +67,9 @@ struct arx_handle {
   // arx_score; consumers join on ev_support_done, producers wait for ev_score_done (operands still being read)
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_support_done = nullptr, ev_score_done = nullptr;
+  // second side stream inside arx_score: the 32-column head projection runs beside the K/V projection and attention
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_done = nullptr;
   bool support_recorded = false, score_recorded = false;
   float *ss_poses = nullptr;       // copy of the support poses when the features were produced on tensor cores
   bool ss_poses_valid = false;
