@@ -48,6 +48,22 @@ __device__ __forceinline__ uint32_t ex2_bits(uint32_t x) {
   return y;
 }
 
+// exp2 of two pre-scaled scores on the FMA pipe instead of the MUFU (the co-limiting pipe): round-to-nearest split
+// x = n + f with the 1.5*2^23 magic constant, 2^f on [-0.5, 0.5] by a degree-3 polynomial (max relative error
+// 7.5e-5, far below the bf16 quantisation of P), exponent add by an integer shift-add.  |x| < 100 is guaranteed by
+// the LayerNorm bound checked at weight load (arx_tc_supported).
+__device__ __forceinline__ void exp2_poly2(uint32_t &a, uint32_t &b) {
+  const uint64_t MAGIC = pack2(12582912.0f, 12582912.0f);
+  const uint64_t x = pack2u(a, b);
+  const uint64_t t = add2(x, MAGIC);
+  const uint64_t f = sub2(x, sub2(t, MAGIC));
+  uint64_t p2 = fma2(f, pack2(0.0551716685f, 0.0551716685f), pack2(0.2426111251f, 0.2426111251f));
+  p2 = fma2(p2, f, pack2(0.6932609677f, 0.6932609677f));
+  p2 = fma2(p2, f, pack2(0.9999280572f, 0.9999280572f));
+  a = (uint32_t)p2 + ((uint32_t)t << 23);
+  b = (uint32_t)(p2 >> 32) + ((uint32_t)(t >> 32) << 23);
+}
+
 // one fp32x2 pair of the epilogue: columns Q, Q+1 (Q even) of chunk registers r; ACC selects one of four accumulators
 template <int Q> __device__ __forceinline__ void epi_pair(const float (&a)[16], const uint64_t (&bb)[8], const uint32_t (&r)[32], uint64_t (&acc)[4]) {
   constexpr int I = arx_slot_i(Q), J = arx_slot_j(Q);
@@ -68,6 +84,8 @@ template <int... Is> __device__ __forceinline__ void zero_pads(uint32_t (&r)[128
   ((r[arx_slot_row_start(2 * Is)] = 0u), ...);
 }
 
+// POLY: every POLY-th register pair of a score tile takes the polynomial exp2 (0 = all on the MUFU)
+template <int POLY>
 __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -245,17 +263,24 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
         }
         if (tr) TRACE3(1 + g, k, 2);
 #pragma unroll
-        for (int j = 0; j < 128; ++j) r[j] = ex2_bits(r[j]);
+        for (int j = 0; j < 128; j += 2) {
+          if (POLY > 0 && (j >> 1) % (POLY > 0 ? POLY : 1) == 0) exp2_poly2(r[j], r[j + 1]);
+          else { r[j] = ex2_bits(r[j]); r[j + 1] = ex2_bits(r[j + 1]); }
+        }
         mbar_arrive(&bars[B_XU + g]);
         zero_pads(r, std::make_integer_sequence<int, 8>{});
-        uint64_t z0 = 0ull, z1 = 0ull;
+        // The sums stay BEHIND the whole MUFU stream (volatile adds): a warp issues in order, and an add that waits
+        // for a fresh MUFU result holds back the next MUFU -- interleaved, the stream ran at ~12 clk per MUFU, not 8.
+        uint64_t z0 = 0ull, z1 = 0ull, z2 = 0ull, z3 = 0ull;
 #pragma unroll
-        for (int q = 0; q < 64; q += 2) {
-          z0 = add2(z0, pack2u(r[2 * q], r[2 * q + 1]));
-          z1 = add2(z1, pack2u(r[2 * q + 2], r[2 * q + 3]));
+        for (int q = 0; q < 64; q += 4) {
+          z0 = add2v(z0, pack2u(r[2 * q], r[2 * q + 1]));
+          z1 = add2v(z1, pack2u(r[2 * q + 2], r[2 * q + 3]));
+          z2 = add2v(z2, pack2u(r[2 * q + 4], r[2 * q + 5]));
+          z3 = add2v(z3, pack2u(r[2 * q + 6], r[2 * q + 7]));
         }
         float zl, zh;
-        unpack2(add2(z0, z1), zl, zh);
+        unpack2(add2(add2(z0, z1), add2(z2, z3)), zl, zh);
         const float zinv = __frcp_rn(zl + zh) * 1.0028177f;       // centred truncation to bf16, see arx_tc2.cu
         const uint64_t zz = pack2(zinv, zinv);
         if (tr) TRACE3(1 + g, k, 3);
@@ -365,8 +390,9 @@ int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
   p.stagger = h->attn_stagger < 0 ? 0 : h->attn_stagger;
   const int groups = (int)((n_win + 1) / 2);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
-  ARX_CUDA(h, cudaFuncSetAttribute(k_attn_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  k_attn_tc3<<<grid, NTHREADS3, SMEM_BYTES, st>>>(p);
+  auto kern = h->attn_poly == 0 ? k_attn_tc3<0> : (h->attn_poly == 2 ? k_attn_tc3<2> : (h->attn_poly == 4 ? k_attn_tc3<4> : k_attn_tc3<3>));
+  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  kern<<<grid, NTHREADS3, SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }
