@@ -342,7 +342,7 @@ int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq,
   const size_t smem = (size_t)(2 * TK * (TM + TPAD) + TM * PS_LD + TM * DF_LD) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    ARX_CUDA(h, cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { const int rc_ = arx_func_smem(h, k_attend, (int)smem); if (rc_) return rc_; }
     attr_set = true;
   }
   for (int64_t b0 = 0; b0 < n_win; b0 += 65535) {
@@ -382,7 +382,7 @@ int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float 
   const int nb = (N + TM - 1) / TM;
   const float scale = 1.0f / sqrtf((float)D);
   const size_t smem = (size_t)(2 * TK * (TM + TPAD) + TM * PS_LD + TM * DF_LD) * sizeof(float);
-  ARX_CUDA(h, cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int rc_ = arx_func_smem(h, k_attend, (int)smem); if (rc_) return rc_; }
   for (int64_t b0 = 0; b0 < n_win; b0 += 65535) {
     int64_t nb_win = n_win - b0 < 65535 ? n_win - b0 : 65535;
     dim3 g(nb, 1, (unsigned)nb_win);

@@ -316,7 +316,7 @@ template <int BN, int OUT, int NSTG> int launch_p(arx_handle *h, GemmPParams &p,
   p.nsta = nsta;
   const uint32_t smem = fixed + nsta * A_SUB;
   auto kern = k_gemm_p<BN, OUT, NSTG>;
-  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int rc_ = arx_func_smem(h, kern, (int)smem); if (rc_) return rc_; }
   int grid = (h->sm_count / p.n_tiles) * p.n_tiles;
   if (grid > p.m_tiles * p.n_tiles) grid = p.m_tiles * p.n_tiles;
   kern<<<grid, P_THREADS, smem, st>>>(p);
@@ -359,7 +359,7 @@ int arx_tuple_img(arx_handle *h, const ArxTransformer &tr, const float *gc, int 
     slots_set = true;
   }
   const uint32_t smem = 65536 + 16 * TI_STRIDE * 4 + 1024 + 128;
-  ARX_CUDA(h, cudaFuncSetAttribute(k_tuple_img, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int rc_ = arx_func_smem(h, k_tuple_img, (int)smem); if (rc_) return rc_; }
   const int64_t grid = n_win < 2 * h->sm_count ? n_win : 2 * h->sm_count;
   TupleParams p{};
   for (int d = 0; d < 128; ++d) { p.gs[d] = tr.ln_host[d] * alpha; p.gs[128 + d] = tr.ln_host[128 + d] * alpha; }

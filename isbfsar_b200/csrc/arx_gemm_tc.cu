@@ -394,7 +394,7 @@ template <int BN, int OUT, int NST = 2> int launch_gemm(arx_handle *h, const Gem
   constexpr uint32_t body = (OUT == OUT_PROJ16 && PROJ_EPI > NST * (A_SUB + BN * 128)) ? PROJ_EPI : NST * (A_SUB + BN * 128);
   constexpr uint32_t smem = body + (2 * NST + 1) * 8 + 16 + 1024;
   auto kern = k_gemm_tc<BN, OUT, NST>;
-  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { const int rc_ = arx_func_smem(h, kern, (int)smem); if (rc_) return rc_; }
   dim3 grid((unsigned)((p.M + 127) / 128), (unsigned)n_tiles);
   ARX_CUDA(h, arx_launch_pdl(kern, grid, dim3(G_THREADS), smem, st, h->pdl, p));
   h->launches++;

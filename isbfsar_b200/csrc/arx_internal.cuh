@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <unordered_map>
 #include "../../include/arx.h"
 
 #define ARX_SOFTMAX_LOG2E 1.4426950408889634f
@@ -101,6 +102,7 @@ struct arx_handle {
   double prof_ms[ARX_N_STAGES] = {0, 0, 0, 0, 0};
   int64_t prof_chunks = 0;
   int last_path = 0;
+  std::unordered_map<const void *, int> smem_attr;   // dynamic shared-memory limit already set per kernel (saves a driver call per launch)
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
   int attn_poly = 0;         // k_attn_tc3: every attn_poly-th register pair takes the FMA-pipe exp2 polynomial (0 = none; debug key 4)
@@ -124,6 +126,16 @@ int arx_fail(arx_handle *h, int code, const char *fmt, ...);
   } while (0)
 
 int arx_ws_reserve(arx_handle *h, size_t bytes);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size instead of once per launch
+template <class K> inline int arx_func_smem(arx_handle *h, K kern, int bytes) {
+  const void *key = reinterpret_cast<const void *>(kern);
+  auto it = h->smem_attr.find(key);
+  if (it != h->smem_attr.end() && it->second == bytes) return ARX_OK;
+  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  h->smem_attr[key] = bytes;
+  return ARX_OK;
+}
 
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor in the stream is
 // still running; it must execute griddepcontrol.wait before touching the predecessor's output.

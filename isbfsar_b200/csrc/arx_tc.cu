@@ -928,7 +928,7 @@ int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_i
   const int grid = groups < h->sm_count ? groups : h->sm_count;
   const bool p_mn = (variant & 1) == 0;     // variant bit 0: use the K-major P layout (2-byte stores) instead of MN-major
   void (*kern)(const AttnParams) = mode0 ? (p_mn ? k_attn_tc<0, true> : k_attn_tc<0, false>) : (p_mn ? k_attn_tc<1, true> : k_attn_tc<1, false>);
-  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  { const int rc_ = arx_func_smem(h, kern, (int)SMEM_BYTES); if (rc_) return rc_; }
   kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   k_finish_tc<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
@@ -974,7 +974,7 @@ int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *
   else if (h->T == 32) kern = k_head_tc<1, 32, false>;
   else return arx_fail(h, ARX_ERR_INVALID, "tc_head: unsupported seq_len");
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
-  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H_SMEM_BYTES));
+  { const int rc_ = arx_func_smem(h, kern, (int)H_SMEM_BYTES); if (rc_) return rc_; }
   kern<<<grid, NTHREADS, H_SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;

@@ -361,7 +361,7 @@ int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
   p.n_win = (int)n_win; p.way = way; p.ldg = g_ld; p.voff = g_voff; p.trace = h->trace_buf;
   const int groups = (int)((n_win + GROUP - 1) / GROUP);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
-  ARX_CUDA(h, cudaFuncSetAttribute(k_attn_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  { const int rc_ = arx_func_smem(h, k_attn_tc2, (int)SMEM_BYTES); if (rc_) return rc_; }
   ARX_CUDA(h, arx_launch_pdl(k_attn_tc2, dim3(grid), dim3(NTHREADS2), SMEM_BYTES, st, h->pdl, p));
   h->launches++;
   return ARX_OK;
@@ -663,7 +663,7 @@ int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *k
   Head2Params p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.uc_img = tr.uc_img; p.uab = uab; p.chosen = chosen; p.y_img = y_img; p.n_win = (int)n_win; p.y_nk = y_nk;
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
-  ARX_CUDA(h, cudaFuncSetAttribute(k_head2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H2_SMEM_BYTES));
+  { const int rc_ = arx_func_smem(h, k_head2_tc, (int)H2_SMEM_BYTES); if (rc_) return rc_; }
   ARX_CUDA(h, arx_launch_pdl(k_head2_tc, dim3(grid), dim3(NTHREADS2), H2_SMEM_BYTES, st, h->pdl, p));
   h->launches++;
   return ARX_OK;

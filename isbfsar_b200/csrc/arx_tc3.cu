@@ -391,7 +391,7 @@ int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
   const int groups = (int)((n_win + 1) / 2);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
   auto kern = h->attn_poly == 0 ? k_attn_tc3<0> : (h->attn_poly == 2 ? k_attn_tc3<2> : (h->attn_poly == 4 ? k_attn_tc3<4> : k_attn_tc3<3>));
-  ARX_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  { const int rc_ = arx_func_smem(h, kern, (int)SMEM_BYTES); if (rc_) return rc_; }
   kern<<<grid, NTHREADS3, SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;

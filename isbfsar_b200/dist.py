@@ -86,15 +86,33 @@ def gather_scores(logits: torch.Tensor, is_true, n_total: int, group=None):
 
 class ScoreGatherer:
     """Preallocated all-gather of equal shards: every rank scores `n_local` windows straight into its slot of a
-    flat `[logits (n_local*way) | is_true (n_local)]` buffer; one `all_gather_into_tensor` per batch, no copies."""
+    flat `[logits (n_local*way) | is_true (n_local)]` buffer; one `all_gather_into_tensor` per batch, no copies.
 
-    def __init__(self, n_local: int, way: int, has_is_true: bool, device, group=None):
+    `depth` > 1 gives that many buffer sets and a communication stream: `gather_async()` enqueues the collective
+    of the batch just scored behind an event, `wait(ticket)` makes the current stream wait for it.  A caller that
+    waits for batch k-1 after scoring batch k overlaps every collective (and the rank skew it absorbs) with the next
+    batch's kernels."""
+
+    def __init__(self, n_local: int, way: int, has_is_true: bool, device, group=None, depth: int = 1):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.n_local, self.way, self.has_is_true = n_local, way, has_is_true
         self.per = n_local * (way + (1 if has_is_true else 0))
-        self.local = torch.empty((self.per,), dtype=torch.float32, device=device)
-        self.all = torch.empty((self.world * self.per,), dtype=torch.float32, device=device) if self.world > 1 else self.local
+        self.depth = max(1, depth)
+        self._local = [torch.empty((self.per,), dtype=torch.float32, device=device) for _ in range(self.depth)]
+        self._all = [torch.empty((self.world * self.per,), dtype=torch.float32, device=device) if self.world > 1 else self._local[i]
+                     for i in range(self.depth)]
+        self._cur = 0
+        self._comm = torch.cuda.Stream(device=device) if (self.depth > 1 and self.world > 1 and torch.device(device).type == "cuda") else None
+        self._done = [None] * self.depth
+
+    @property
+    def local(self):
+        return self._local[self._cur]
+
+    @property
+    def all(self):
+        return self._all[self._cur]
 
     def _views(self, flat):
         lo = flat[: self.n_local * self.way].view(self.n_local, self.way)
@@ -105,11 +123,41 @@ class ScoreGatherer:
         """(logits, is_true) views of this rank's slot: pass as `out=` to `scorer.score`."""
         return self._views(self.local)
 
+    def _result(self, i):
+        return [self._views(self._all[i][r * self.per:(r + 1) * self.per]) for r in range(self.world)]
+
     def gather(self):
         """-> list over ranks of (logits (n_local,way), is_true (n_local,1)) views of the gathered buffer."""
         if self.world > 1:
             dist.all_gather_into_tensor(self.all, self.local, group=self.group)
-        return [self._views(self.all[r * self.per:(r + 1) * self.per]) for r in range(self.world)]
+        return self._result(self._cur)
+
+    def gather_async(self):
+        """Enqueue the all-gather of the batch just scored into the current buffer set on the communication stream and
+        advance to the next set.  Returns a ticket for `wait`."""
+        i = self._cur
+        if self._comm is None:
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._all[i], self._local[i], group=self.group)
+        else:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(ready)
+                if self.world > 1:
+                    dist.all_gather_into_tensor(self._all[i], self._local[i], group=self.group)
+                done = torch.cuda.Event()
+                done.record()
+            self._done[i] = done
+        self._cur = (i + 1) % self.depth
+        return i
+
+    def wait(self, ticket):
+        """Make the current stream wait for the collective of `ticket`; -> the per-rank views (valid until the
+        buffer set comes round again, `depth` batches later)."""
+        if self._done[ticket] is not None:
+            torch.cuda.current_stream().wait_event(self._done[ticket])
+        return self._result(ticket)
 
 
 def score_sharded(scorer, query_full_or_local, n_total: int, local: bool = False, group=None):

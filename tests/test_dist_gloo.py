@@ -86,3 +86,47 @@ def test_sharded_scoring_world2(B):
         assert logits.shape == (B, 5) and is_true.shape == (B, 1)
         np.testing.assert_allclose(logits, lo, rtol=1e-5, atol=1e-6)      # every rank holds the full result
         np.testing.assert_allclose(is_true, it, rtol=1e-5, atol=1e-6)
+
+
+def _gatherer_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from isbfsar_b200.dist import ScoreGatherer
+        n_local, way = 6, 5
+        g = ScoreGatherer(n_local, way, True, "cpu", depth=2)
+        tickets, got = [], []
+        for k in range(4):                      # pipelined: the collective of batch k is joined after batch k+1
+            lo, it = g.out()
+            lo.copy_(torch.full((n_local, way), 100.0 * k + rank))
+            it.copy_(torch.full((n_local, 1), 100.0 * k + rank + 0.5))
+            tickets.append(g.gather_async())
+            if len(tickets) > 1:
+                got.append([(a.clone(), b.clone()) for a, b in g.wait(tickets.pop(0))])
+        got.append([(a.clone(), b.clone()) for a, b in g.wait(tickets.pop(0))])
+        ok = len(got) == 4
+        for k, per_rank in enumerate(got):
+            for r, (lo, it) in enumerate(per_rank):
+                ok = ok and bool((lo == 100.0 * k + r).all()) and bool((it == 100.0 * k + r + 0.5).all())
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipelined_score_gatherer_world2():
+    """ScoreGatherer with two buffer sets: batch k's all-gather is joined one batch later; every rank sees every shard."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
