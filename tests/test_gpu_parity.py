@@ -363,10 +363,12 @@ def test_t8_runs_on_generic_tensor_core_kernels():
     assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
 
 
-@pytest.mark.parametrize("variant", [8, 8 + 1, 8 + 2, 4, 16])
+@pytest.mark.parametrize("variant", [8, 8 + 1, 8 + 2, 4, 16, 32, 128, 512, 1024, 2048])
 def test_kernel_variants_agree(variant):
     """Bring-up variants stay green: first-generation attention kernel (8), its K-major P layout (+1), fp32
-    open-set head (+2), fp32 linear layers (4), unfused projection (16)."""
+    open-set head (+2), fp32 linear layers (4), unfused projection (16), first-generation head pass (32),
+    second-generation attention (128), tuple build inside the projection GEMM epilogue (512), one-tile-per-CTA
+    frame-MLP GEMMs (1024), head projection on the caller's stream (2048)."""
     cfg = Cfg()
     m, sd = make_model(cfg, 0)
     support, labels, query, _ = make_episode(cfg, 131, 91, "structured")
@@ -376,6 +378,38 @@ def test_kernel_variants_agree(variant):
     logits, is_true = m.score(torch.from_numpy(query).cuda())
     assert m.last_path() == 2
     assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
+
+
+@pytest.mark.parametrize("key,value", [(3, 0), (3, 1000), (4, 2), (4, 3)])
+def test_attention_schedule_knobs_agree(key, value):
+    """Softmax-group scheduling (free-running / staggered instead of the MUFU token) and the FMA-pipe exp2 share of
+    the attention kernel change timing, not results (odd window count: exercises the single-window tail group)."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 333, 92, "structured")
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    m.debug_set(key, value)
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2
+    assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
+
+
+def test_persistent_gemm_path_large_batch():
+    """Batches of >= 2 row tiles per SM take the persistent weight-resident frame-MLP GEMMs; same scores as the
+    one-tile-per-CTA kernels (variant 1024) on the same windows, and parity with the oracle on a sample."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    n = 2 * 148 * 8 + 13                      # > 2 tiles per SM, ragged tail
+    support, labels, query, _ = make_episode(cfg, n, 93, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    Q = torch.from_numpy(query).cuda()
+    a_lo, a_it = m.score(Q)
+    m.debug_set(0, 1024)
+    b_lo, b_it = m.score(Q)
+    assert torch.equal(a_lo, b_lo) and torch.equal(a_it, b_it)
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query[-64:])
+    assert rel_err(a_lo[-64:].cpu(), lo).max() < TOL_TC and rel_err(a_it[-64:].cpu(), it).max() < TOL_TC
 
 
 def test_streaming_host_api_matches_device_path():
