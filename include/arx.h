@@ -178,7 +178,9 @@ ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t
  *         (default), >= 0 free-running with group 1 started this many clocks late.
  *  key 4: attention kernel: every value-th register pair of a score tile takes the FMA-pipe exp2 polynomial
  *         instead of MUFU.EX2 (0 = none (default), 2, 3, 4; measured: no gain on B200, the packed FMA ops cost
- *         as much pipe time as the MUFU they replace). */
+ *         as much pipe time as the MUFU they replace).
+ *  key 5: CUDA-graph replay of the arx_score kernel chain when its arguments recur (default on; the environment
+ *         variable ARX_GRAPHS=0 disables it too). */
 ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
 /* key 1 (value != 0) arms a timeline trace of CTA 0 of the attention kernel; this reads it back:
  * host_out[3 roles][64 tiles][8 stamps] of SM clock values (bring-up tool). */

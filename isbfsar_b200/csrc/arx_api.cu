@@ -73,6 +73,7 @@ int upload(arx_handle *h, float *dst, const float *src, size_t n, bool on_device
 }
 
 void free_support(arx_handle *h) {
+  h->support_gen++;      // operand pointers change: cached score graphs no longer match
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
     cudaFree(h->tr[i].ks); cudaFree(h->tr[i].vs);
     cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img); cudaFree(h->tr[i].vs_img_bf); cudaFree(h->tr[i].uc_img);
@@ -240,6 +241,7 @@ void arx_destroy(arx_handle *h) {
     if (h->hs_ev_done[i]) cudaEventDestroy(h->hs_ev_done[i]);
   }
   if (h->hs_h2d) { cudaStreamDestroy(h->hs_h2d); cudaStreamDestroy(h->hs_comp); cudaStreamDestroy(h->hs_d2h); }
+  for (auto &g : h->graphs) for (int i = 0; i < 2; ++i) if (g.exec[i]) cudaGraphExecDestroy(g.exec[i]);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->ev_aux_fork) cudaEventDestroy(h->ev_aux_fork);
@@ -338,6 +340,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
   }
   ARX_CUDA(h, cudaStreamSynchronize(st));
   h->weights_loaded = true;
+  h->weights_gen++;
   free_support(h);   // support operands depend on the weights
   return ARX_OK;
 }
@@ -618,6 +621,57 @@ static int prof_mark(arx_handle *h, int idx, cudaStream_t st) {
   return ARX_OK;
 }
 
+extern "C++" {
+static bool graphs_enabled(arx_handle *h) {
+  if (h->graphs_on < 0) {
+    const char *e = getenv("ARX_GRAPHS");
+    h->graphs_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return h->graphs_on == 1;
+}
+
+static ArxScoreGraph *score_graph_lookup(arx_handle *h, const ArxScoreGraphKey &key) {
+  h->graph_tick++;
+  for (auto &g : h->graphs)
+    if (g.key == key) { g.last_use = h->graph_tick; return &g; }
+  if (h->graphs.size() >= 8) {                     // evict the least recently used entry
+    size_t v = 0;
+    for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[v].last_use) v = i;
+    for (int i = 0; i < 2; ++i) if (h->graphs[v].exec[i]) cudaGraphExecDestroy(h->graphs[v].exec[i]);
+    h->graphs.erase(h->graphs.begin() + v);
+  }
+  ArxScoreGraph g;
+  g.key = key;
+  g.last_use = h->graph_tick;
+  h->graphs.push_back(g);
+  return &h->graphs.back();
+}
+
+// Run one segment of the score chain: eagerly the first time a key is seen (one-time initialisation -- symbol
+// uploads, function attributes, allocations -- must not happen under capture), captured into a graph the second
+// time, replayed from then on.
+template <class F> static int score_segment(arx_handle *h, ArxScoreGraph *g, int seg, cudaStream_t st, F &&body) {
+  if (!g || g->seen < 1) return body();
+  if (!g->exec[seg]) {
+    const int64_t l0 = h->launches;
+    ARX_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || !graph) return arx_fail(h, ARX_ERR_CUDA, "score: stream capture failed: %s", cudaGetErrorString(e));
+    const cudaError_t e2 = cudaGraphInstantiate(&g->exec[seg], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { g->exec[seg] = nullptr; return arx_fail(h, ARX_ERR_CUDA, "score: graph instantiation failed: %s", cudaGetErrorString(e2)); }
+    g->launches[seg] = h->launches - l0;
+    h->launches = l0;
+  }
+  ARX_CUDA(h, cudaGraphLaunch(g->exec[seg], st));
+  h->launches += g->launches[seg];
+  return ARX_OK;
+}
+}  // extern "C++"
+
 static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
                       float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st) {
   if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score: weights not loaded");
@@ -659,12 +713,22 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   if (st != h->hs_comp && h->hs_submitted > 0)      // the shared workspace may still be in use by streamed requests
     ARX_CUDA(h, cudaStreamWaitEvent(st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0));
   bool aux_pending = false;
+  ArxScoreGraph *sg = nullptr;
+  const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;     // the default streams cannot be captured
+  if (capturable && use_tc && split_proj && head2 && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf && graphs_enabled(h)) {
+    ArxScoreGraphKey key;
+    key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
+    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0); key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
+    sg = score_graph_lookup(h, key);
+  }
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
     const int64_t n = std::min(chunk, n_windows - b0);
     const float *FE;
     if ((rc = prof_mark(h, 0, st))) return rc;
     const int64_t rows = n * h->T;
     const int f_nk = tr.tl_proj.nk, f_onehot = tr.table_in_gemm ? f_nk - 1 : -1;     // feature image: + one-hot sub-tile
+    rc = score_segment(h, sg, 0, st, [&]() -> int {
+    int rc = ARX_OK;
     if (tcl) {
       // frame MLP + projection on tensor cores, activations chained as fp16 images
       FE = nullptr;
@@ -693,7 +757,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
           return rc;
         if (head2) {
           // only the head pass reads these 32 columns: run them on a second stream, beside projection + attention
-          const bool aux = (h->tc_variant & 2048) == 0 && !h->prof_on;
+          const bool aux = (h->tc_variant & 2048) == 0 && !h->prof_on && !sg;      // (a graph segment must end joined)
           cudaStream_t us = st;
           if (aux) {
             if (!h->aux_stream) {
@@ -723,11 +787,16 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     if ((rc = prof_mark(h, 2, st))) return rc;
     if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
     if (use_tc && !fused_proj && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
+    return ARX_OK;
+    });
+    if (rc) return rc;
     if ((rc = support_wait(h, st))) return rc;                   // join the support chain (side stream) before its operands are read
 
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
     const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
+    rc = score_segment(h, sg, 1, st, [&]() -> int {
+    int rc = ARX_OK;
     if (use_tc) {
       if ((rc = arx_tc_attention(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, w.partial, logits_dev + b0 * way, ch,
                                  h->tc_variant, g_ld, g_voff, split_proj, st)))
@@ -755,8 +824,12 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
       if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
       if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
     }
+    return ARX_OK;
+    });
+    if (rc) return rc;
     if ((rc = prof_mark(h, 5, st))) return rc;
   }
+  if (sg) sg->seen++;
   if (h->ev_score_done) {
     ARX_CUDA(h, cudaEventRecord(h->ev_score_done, st));
     h->score_recorded = true;
@@ -951,6 +1024,7 @@ int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
   if (key == 2) { h->pdl = value != 0; return ARX_OK; }
   if (key == 3) { h->attn_stagger = (int)value; return ARX_OK; }
   if (key == 4) { h->attn_poly = (int)value; return ARX_OK; }
+  if (key == 5) { h->graphs_on = value != 0; return ARX_OK; }
   if (key == 1) {   // allocate (value != 0) / free the kernel timeline trace buffer: 3 roles x 64 tiles x 8 stamps
     if (value && !h->trace_buf) {
       ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->trace_buf), 3 * 64 * 8 * sizeof(long long)));

@@ -43,6 +43,27 @@ struct ArxTransformer {
   __half *uc_img = nullptr;  // per class Wdr.Vc^T (16 x 128 fp16 B operand)
 };
 
+// Replayable CUDA graphs of the arx_score kernel chain for one (buffers, batch, support geometry, weights) key: the
+// ~14 launches of a score become two graph launches (before / after the join with the support chain), which takes
+// the host off the critical path when several ranks share the box's cores.
+struct ArxScoreGraphKey {
+  const void *q = nullptr, *lo = nullptr, *it = nullptr, *ch = nullptr, *ws = nullptr;
+  int64_t n = 0;
+  int way = 0, variant = 0, poly = 0, stagger = 0;
+  uint64_t sgen = 0, wgen = 0;
+  bool operator==(const ArxScoreGraphKey &o) const {
+    return q == o.q && lo == o.lo && it == o.it && ch == o.ch && ws == o.ws && n == o.n && way == o.way && variant == o.variant &&
+           poly == o.poly && stagger == o.stagger && sgen == o.sgen && wgen == o.wgen;
+  }
+};
+struct ArxScoreGraph {
+  ArxScoreGraphKey key;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  int64_t launches[2] = {0, 0};
+  int seen = 0;
+  uint64_t last_use = 0;
+};
+
 struct arx_handle {
   arx_config cfg{};
   int device = 0;
@@ -102,6 +123,9 @@ struct arx_handle {
   double prof_ms[ARX_N_STAGES] = {0, 0, 0, 0, 0};
   int64_t prof_chunks = 0;
   int last_path = 0;
+  std::vector<ArxScoreGraph> graphs;     // small LRU cache (arx_score with recurring arguments)
+  uint64_t graph_tick = 0, support_gen = 0, weights_gen = 0;
+  int graphs_on = -1;                    // -1: from the environment (ARX_GRAPHS=0 disables), else 0/1 (debug key 5)
   std::unordered_map<const void *, int> smem_attr;   // dynamic shared-memory limit already set per kernel (saves a driver call per launch)
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)

@@ -8,6 +8,7 @@ cfg = Cfg(); m, sd = make_model(cfg, 0)
 support, labels, query, _ = make_episode(cfg, 4096, 1, "structured")
 S = torch.from_numpy(support[0]).cuda(); Q = torch.from_numpy(query).cuda()
 out = (torch.empty((4096, 5), device="cuda"), torch.empty((4096, 1), device="cuda"))
+torch.cuda.set_stream(torch.cuda.Stream())
 for prof in (False, True):
     m.profile(prof)
     for _ in range(5):
