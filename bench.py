@@ -197,6 +197,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the only collective is a 24-byte-per-window all-gather that overlaps the next batch's persistent kernels (one
+        # CTA per SM, whole register file): keep NCCL's footprint to a couple of CTAs and let them in first
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = Cfg()
