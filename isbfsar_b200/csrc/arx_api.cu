@@ -714,7 +714,11 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     ARX_CUDA(h, cudaStreamWaitEvent(st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0));
   bool aux_pending = false;
   ArxScoreGraph *sg = nullptr;
-  const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;     // the default streams cannot be captured
+  bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;     // the default streams cannot be captured
+  if (capturable && graphs_enabled(h)) {              // a caller that is capturing this stream itself gets plain launches
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { (void)cudaGetLastError(); capturable = false; }
+  }
   if (capturable && use_tc && split_proj && head2 && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf && graphs_enabled(h)) {
     ArxScoreGraphKey key;
     key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
