@@ -58,7 +58,9 @@ def emulate(cfg, sd, support, query, fmt):
 
 def main():
     B = int(os.environ.get("B", 512))
-    cfg = Cfg()
+    # CFG=t32: BASELINE cfg4 pairs (20-way, T=32, N=496) -- does the same operand scheme hold for the N > 128 tiling?
+    cfg = Cfg(way=20, seq_len=32, temp_set=[2, 3]) if os.environ.get("CFG") == "t32" else Cfg()
+    only = os.environ.get("SCHEMES")
     schemes = {
       "all-fp32":   dict(mlp_a="fp32", mlp_w="fp32", proj_a="fp32", proj_w="fp32", qk="fp32", pv="fp32", disc="fp32"),
       "all-bf16":   dict(mlp_a="bf16", mlp_w="bf16", proj_a="bf16", proj_w="bf16", qk="bf16", pv="bf16", disc="bf16"),
@@ -82,6 +84,8 @@ def main():
         srt = np.sort(l64, 1); margin = (srt[:, -1] - srt[:, -2]) / np.abs(srt[:, -1])
         print(f"== affine={affine} kind={kind} B={B}  margin p0.1={np.quantile(margin,0.001):.2e} min={margin.min():.2e}; oracle32 vs 64: {np.abs(l32/l64-1).max():.2e}")
         for name, fmt in schemes.items():
+            if only and name not in only.split(";"):
+                continue
             l, t = emulate(cfg, sd, support, query, fmt)
             rel = np.abs(l / l64 - 1)
             relw = rel[np.arange(B), l64.argmax(1)]
