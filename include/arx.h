@@ -122,6 +122,18 @@ ARX_API int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way,
 ARX_API int arx_score(arx_handle *h, const float *query_dev, int64_t n_windows,
               float *logits_dev, float *is_true_dev, int32_t *chosen_dev, void *stream);
 
+/* TRXOS.forward in the training / evaluation call shape (modules/ar/utils/train.py:110-120,
+ * modules/ar/utils/test/compute_fsos.py:89-98): every batch row is its own EPISODE -- query i is scored against
+ * ITS OWN `way` support classes (model.py:59-148 never mixes batch rows).  All episodes go through the batched
+ * kernels at once (the support operands of the n_episodes*way classes form one pool; window i attends classes
+ * [i*way, (i+1)*way) of it).
+ *   support_dev (n_episodes, way, T, 3J) poses, or (n_episodes, way, T, F) frame features when is_features != 0
+ *   (the ss_features argument); query_dev (n_episodes, T, 3J); outputs as arx_score.
+ * REPLACES the handle's current support set (by the pool of the last pass): call arx_set_support_* again before
+ * the next arx_score. */
+ARX_API int arx_score_episodes(arx_handle *h, const float *support_dev, int32_t is_features, int32_t way, const float *query_dev,
+                       int64_t n_episodes, float *logits_dev, float *is_true_dev, int32_t *chosen_dev, void *stream);
+
 /* TemporalCrossTransformer(args, temp_set[ti]).forward(...)['logits'] (model.py:59-148)
  * from precomputed frame features qfeats_dev (B,T,F); used for the cardinality-3
  * transformer that TRXOS.forward never calls (model.py:320). */

@@ -53,9 +53,20 @@ class ActionRecognizer:
         self._q = None
         self._outs = None
 
-    # the support operands on the device are valid for exactly this identity of the support set
+    # The support operands on the device are valid for exactly this content identity of the support set.  The host
+    # app replaces the dict wholesale (main.py:321-333 `load`) and could edit tensors in place, so the key is built from
+    # storage address + version counter + shape of every tensor (a freed-and-reused `id()` or an in-place edit cannot
+    # alias), not from object identity.
+    @staticmethod
+    def _tkey(t):
+        if t is None:
+            return None
+        if isinstance(t, torch.Tensor):
+            return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+        return ("obj", id(t))
+
     def _current_key(self):
-        return tuple((k, id(v.get("poses")), id(v.get("features"))) for k, v in self.support_set.items())
+        return tuple((k, self._tkey(v.get("poses")), self._tkey(v.get("features"))) for k, v in self.support_set.items())
 
     def inference(self, data):
         """ar.py:30-84.  data = {"sk": ndarray (3J,)}.  Returns (results, open_set_result, requires_focus)."""

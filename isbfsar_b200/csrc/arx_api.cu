@@ -379,7 +379,7 @@ static int support_fork(arx_handle *h, cudaStream_t st, cudaStream_t *side) {
     ARX_CUDA(h, cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_support_done, cudaEventDisableTiming));
-    ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
+    if (!h->ev_score_done) ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
   }
   ARX_CUDA(h, cudaEventRecord(h->ev_fork, st));
   ARX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
@@ -672,8 +672,10 @@ template <class F> static int score_segment(arx_handle *h, ArxScoreGraph *g, int
 }
 }  // extern "C++"
 
+#define ARX_EP_UNSUPPORTED (-100)   /* internal: episode mode asked for a shape the batched kernels do not cover */
+// ep_way > 0: episode mode -- window b is scored against classes [b*ep_way, (b+1)*ep_way) of the support pool
 static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
-                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st) {
+                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st, int ep_way = 0) {
   if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score: weights not loaded");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score: support set not set");
   if (n_windows == 0) return ARX_OK;
@@ -682,7 +684,8 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const bool disc = is_true_dev != nullptr;
   if (disc && (!h->cfg.has_discriminator || ti != 0 || tr.c != 2))
     return arx_fail(h, ARX_ERR_INVALID, "score: the discriminator is sized for pair tuples of transformers[0] (model.py:283-285)");
-  const int way = h->way;
+  const int way = ep_way > 0 ? ep_way : h->way;
+  if (ep_way > 0 && (int64_t)ep_way * n_windows != h->way) return arx_fail(h, ARX_ERR_STATE, "score: episode pool does not match the batch");
   const bool debug_out = probs || protos;
   bool use_tc = h->cfg.force_path != 1 && !debug_out && arx_tc_supported(h, tr) && tr.ks_img != nullptr;
   if (h->cfg.force_path == 2 && !use_tc && !debug_out)
@@ -703,6 +706,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const bool big_batch = n_windows * h->T >= 128ll * 2 * h->sm_count;             // persistent GEMMs pay off from ~2 tiles per SM
   const bool p_embed = tcl && big_batch && (h->tc_variant & 1024) == 0 && arx_tcp_supported(h->tl_fc1) && arx_tcp_supported(h->tl_fc2);
   const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32, tcl, tc_head);
+  if (ep_way > 0 && !(use_tc && split_proj && (!disc || head2) && from_frames && chunk >= n_windows && (h->tc_variant & 128) == 0)) return ARX_EP_UNSUPPORTED;
   Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32, tcl, tc_head);
   size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
   int rc = arx_ws_reserve(h, sz.bytes + extra);
@@ -712,6 +716,8 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   h->last_path = use_tc ? 2 : 1;
   if (st != h->hs_comp && h->hs_submitted > 0)      // the shared workspace may still be in use by streamed requests
     ARX_CUDA(h, cudaStreamWaitEvent(st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0));
+  // ... or by a scoring pass enqueued on ANOTHER stream (one workspace per handle): order this pass behind it
+  if (h->score_recorded && h->last_score_stream != st) ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_score_done, 0));
   bool aux_pending = false;
   ArxScoreGraph *sg = nullptr;
   bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;     // the default streams cannot be captured
@@ -722,7 +728,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   if (capturable && use_tc && split_proj && head2 && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf && graphs_enabled(h)) {
     ArxScoreGraphKey key;
     key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
-    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0); key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
+    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0); key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
     sg = score_graph_lookup(h, key);
   }
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
@@ -803,12 +809,12 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     int rc = ARX_OK;
     if (use_tc) {
       if ((rc = arx_tc_attention(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, w.partial, logits_dev + b0 * way, ch,
-                                 h->tc_variant, g_ld, g_voff, split_proj, st)))
+                                 h->tc_variant, g_ld, g_voff, split_proj, ep_way > 0, st)))
         return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
       if (disc && head2) {
         if (aux_pending) { ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_aux_done, 0)); aux_pending = false; }
-        if ((rc = arx_tc2_head_launch(h, tr, w.kq_img, w.uab, n, ch, w.y_img, h->tl_d1.nk, st))) return rc;
+        if ((rc = arx_tc2_head_launch(h, tr, w.kq_img, w.uab, n, ch, w.y_img, h->tl_d1.nk, ep_way, st))) return rc;
       } else if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
                                                                h->tl_d1.nk, g_ld, g_voff, st)))
         return rc;
@@ -834,10 +840,10 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     if ((rc = prof_mark(h, 5, st))) return rc;
   }
   if (sg) sg->seen++;
-  if (h->ev_score_done) {
-    ARX_CUDA(h, cudaEventRecord(h->ev_score_done, st));
-    h->score_recorded = true;
-  }
+  if (!h->ev_score_done) ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
+  ARX_CUDA(h, cudaEventRecord(h->ev_score_done, st));
+  h->score_recorded = true;
+  h->last_score_stream = st;
   return ARX_OK;
 }
 
@@ -847,6 +853,36 @@ int arx_score(arx_handle *h, const float *query_dev, int64_t n_windows, float *l
   if (!h->cfg.has_discriminator) is_true_dev = nullptr;
   return score_impl(h, 0, query_dev, nullptr, n_windows, logits_dev, is_true_dev, chosen_dev, nullptr, nullptr,
                     static_cast<cudaStream_t>(stream));
+}
+
+int arx_score_episodes(arx_handle *h, const float *support_dev, int32_t is_features, int32_t way, const float *query_dev, int64_t n_episodes,
+                       float *logits_dev, float *is_true_dev, int32_t *chosen_dev, void *stream) {
+  if (!h || !support_dev || !query_dev || !logits_dev || way < 1 || n_episodes < 0) return arx_fail(h, ARX_ERR_INVALID, "score_episodes: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score_episodes: weights not loaded");
+  if (!h->cfg.has_discriminator) is_true_dev = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t per_class = (size_t)h->T * (is_features ? h->F : h->J3);
+  const int64_t piece = 256;                 // episodes per pass: the pool holds piece*way classes of support operands
+  for (int64_t e0 = 0; e0 < n_episodes; e0 += piece) {
+    const int64_t m = std::min(piece, n_episodes - e0);
+    const float *sup = support_dev + (size_t)e0 * way * per_class;
+    int rc = is_features ? arx_set_support_features(h, sup, (int32_t)(m * way), stream) : arx_set_support_poses(h, sup, (int32_t)(m * way), stream);
+    if (rc) return rc;
+    rc = score_impl(h, 0, query_dev + (size_t)e0 * h->T * h->J3, nullptr, m, logits_dev + e0 * way, is_true_dev ? is_true_dev + e0 : nullptr,
+                    chosen_dev ? chosen_dev + e0 : nullptr, nullptr, nullptr, st, way);
+    if (rc == ARX_EP_UNSUPPORTED) {
+      // shapes without the batched-episode kernels (other T / cardinality / fp32 path): one episode at a time, same kernels as arx_score
+      for (int64_t e = e0; e < e0 + m; ++e) {
+        const float *se = support_dev + (size_t)e * way * per_class;
+        rc = is_features ? arx_set_support_features(h, se, way, stream) : arx_set_support_poses(h, se, way, stream);
+        if (rc) return rc;
+        rc = score_impl(h, 0, query_dev + (size_t)e * h->T * h->J3, nullptr, 1, logits_dev + e * way, is_true_dev ? is_true_dev + e : nullptr,
+                        chosen_dev ? chosen_dev + e : nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+      }
+    } else if (rc) return rc;
+  }
+  return ARX_OK;
 }
 
 int arx_score_features(arx_handle *h, int32_t ti, const float *qfeats_dev, int64_t n_windows, float *logits_dev, void *stream) {
@@ -950,7 +986,7 @@ int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_wind
     }
     h->hs_cap_windows = n_windows;
     h->hs_way = way;
-    h->hs_submitted = 0;
+    h->hs_base = h->hs_submitted;      // ticket ids stay monotonic; everything before the device-wide sync above has completed
   }
   const int64_t id = h->hs_submitted;
   const int s = (int)(id % ARX_HOST_DEPTH);
@@ -959,13 +995,14 @@ int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_wind
   float *dist = dlog + (size_t)n_windows * way;
   int32_t *dch = reinterpret_cast<int32_t *>(dist + n_windows);
   // H2D of request id may start once the request that used this slot (id - DEPTH) has been scored
-  if (id >= ARX_HOST_DEPTH) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_h2d, h->hs_ev_comp[s], 0));
+  const bool slot_used = id - h->hs_base >= ARX_HOST_DEPTH;     // this slot's buffers carried an earlier request since the last reallocation
+  if (slot_used) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_h2d, h->hs_ev_comp[s], 0));
   ARX_CUDA(h, cudaMemcpyAsync(din, query_host, n_windows * in_per, cudaMemcpyHostToDevice, h->hs_h2d));
   ARX_CUDA(h, cudaEventRecord(h->hs_ev_h2d[s], h->hs_h2d));
   // scoring: after its inputs arrived and after the results previously held in this slot went back to the host
   ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_h2d[s], 0));
   if (h->score_recorded) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->ev_score_done, 0));     // workspace shared with arx_score callers
-  if (id >= ARX_HOST_DEPTH) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_done[s], 0));
+  if (slot_used) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_done[s], 0));
   int rc = score_impl(h, 0, din, nullptr, n_windows, dlog, disc ? dist : nullptr, dch, nullptr, nullptr, h->hs_comp);
   if (rc) return rc;
   ARX_CUDA(h, cudaEventRecord(h->hs_ev_comp[s], h->hs_comp));
@@ -981,7 +1018,9 @@ int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_wind
 
 int arx_score_host_wait(arx_handle *h, int64_t ticket) {
   if (!h || ticket < 0 || ticket >= h->hs_submitted) return arx_fail(h, ARX_ERR_INVALID, "score_host_wait: unknown ticket");
-  if (ticket + ARX_HOST_DEPTH < h->hs_submitted) return ARX_OK;       // its slot has been reused: it completed long ago
+  if (ticket < h->hs_base) return ARX_OK;       // submitted before a staging reallocation, which synchronised the device
+  // The slot's event may have been re-recorded for a newer request (submit never blocks the host): the copy-back
+  // stream is in order, so that newer record completing implies this ticket's copies have landed too.
   ARX_CUDA(h, cudaEventSynchronize(h->hs_ev_done[ticket % ARX_HOST_DEPTH]));
   return ARX_OK;
 }

@@ -340,11 +340,7 @@ int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq,
   const int nb = (N + TM - 1) / TM;
   const float scale = 1.0f / sqrtf((float)D);
   const size_t smem = (size_t)(2 * TK * (TM + TPAD) + TM * PS_LD + TM * DF_LD) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    { const int rc_ = arx_func_smem(h, k_attend, (int)smem); if (rc_) return rc_; }
-    attr_set = true;
-  }
+  { const int rc_ = arx_func_smem(h, k_attend, (int)smem); if (rc_) return rc_; }      // cached per handle (per device)
   for (int64_t b0 = 0; b0 < n_win; b0 += 65535) {
     int64_t nb_win = n_win - b0 < 65535 ? n_win - b0 : 65535;
     for (int c0 = 0; c0 < way; c0 += 65535) {  // way never exceeds this; kept for form

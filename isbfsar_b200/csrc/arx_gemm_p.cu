@@ -351,12 +351,11 @@ int arx_tcp_linear_chunked(arx_handle *h, const ArxTcLinear &L, const __half *a_
 // Kq operand images of n_win query windows from the chunked per-frame K projections (T=16 pair tuples, slot order)
 int arx_tuple_img(arx_handle *h, const ArxTransformer &tr, const float *gc, int n_chunks, int64_t n_win, __half *kq_img, float alpha,
                   cudaStream_t st) {
-  static bool slots_set = false;
-  if (!slots_set) {
+  if (!(h->dev_init & ARX_INIT_PSLOTS)) {         // __constant__ symbols are per device: once per handle, not per process
     int32_t slots[256];
     arx_tc2_slot_table(slots);
     ARX_CUDA(h, cudaMemcpyToSymbol(c_pslots, slots, sizeof(slots)));
-    slots_set = true;
+    h->dev_init |= ARX_INIT_PSLOTS;
   }
   const uint32_t smem = 65536 + 16 * TI_STRIDE * 4 + 1024 + 128;
   { const int rc_ = arx_func_smem(h, k_tuple_img, (int)smem); if (rc_) return rc_; }

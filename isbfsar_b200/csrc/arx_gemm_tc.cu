@@ -462,10 +462,9 @@ int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_im
   if (L.BN != 256 || L.n_tiles != 2) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: needs a 512-column projection");
   (void)table_sums;
   if (table) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: the positional table must come in through the one-hot K columns");
-  static bool slots_set = false;
-  if (!slots_set) {
+  if (!(h->dev_init & ARX_INIT_QSLOTS)) {
     ARX_CUDA(h, cudaMemcpyToSymbol(c_qslots, slots_host, 256 * sizeof(int)));
-    slots_set = true;
+    h->dev_init |= ARX_INIT_QSLOTS;
   }
   GemmParams p{};
   p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;

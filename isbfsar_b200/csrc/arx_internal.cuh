@@ -93,6 +93,7 @@ struct arx_handle {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_aux_fork = nullptr, ev_aux_done = nullptr;
   bool support_recorded = false, score_recorded = false;
+  cudaStream_t last_score_stream = nullptr;   // stream of the last scoring pass (ev_score_done was recorded there)
   float *ss_poses = nullptr;       // copy of the support poses when the features were produced on tensor cores
   bool ss_poses_valid = false;
   bool ss_feat_valid = false;      // ss_feat holds fp32 features (else they are derived lazily from ss_poses)
@@ -113,7 +114,7 @@ struct arx_handle {
   void *hs_in[ARX_HOST_DEPTH] = {nullptr, nullptr};
   void *hs_out[ARX_HOST_DEPTH] = {nullptr, nullptr};
   cudaEvent_t hs_ev_h2d[ARX_HOST_DEPTH] = {nullptr, nullptr}, hs_ev_comp[ARX_HOST_DEPTH] = {nullptr, nullptr}, hs_ev_done[ARX_HOST_DEPTH] = {nullptr, nullptr};
-  int64_t hs_cap_windows = 0, hs_submitted = 0;
+  int64_t hs_cap_windows = 0, hs_submitted = 0, hs_base = 0;   // tickets below hs_base predate the last staging reallocation
   int hs_way = 0;
   int64_t launches = 0;
   // stage timers (arx_profile_*)
@@ -126,6 +127,9 @@ struct arx_handle {
   std::vector<ArxScoreGraph> graphs;     // small LRU cache (arx_score with recurring arguments)
   uint64_t graph_tick = 0, support_gen = 0, weights_gen = 0;
   int graphs_on = -1;                    // -1: from the environment (ARX_GRAPHS=0 disables), else 0/1 (debug key 5)
+  // one-time per-DEVICE initialisation done by this handle (__constant__ tables, function attributes): kept per handle,
+  // not process-wide, so a second handle on another GPU of the same process initialises its own device
+  uint32_t dev_init = 0;
   std::unordered_map<const void *, int> smem_attr;   // dynamic shared-memory limit already set per kernel (saves a driver call per launch)
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
@@ -150,6 +154,7 @@ int arx_fail(arx_handle *h, int code, const char *fmt, ...);
   } while (0)
 
 int arx_ws_reserve(arx_handle *h, size_t bytes);
+enum ArxDevInit { ARX_INIT_PSLOTS = 1, ARX_INIT_QSLOTS = 2, ARX_INIT_SLOT_RANK = 4, ARX_INIT_FP32_ATTN = 8 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size instead of once per launch
 template <class K> inline int arx_func_smem(arx_handle *h, K kern, int bytes) {
@@ -198,7 +203,8 @@ int arx_tc_support_build(arx_handle *h, ArxTransformer &tr, const float *G, int 
 int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st);
 bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, cudaStream_t st);
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, bool episodes,
+                     cudaStream_t st);
 
 bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st);
@@ -247,14 +253,14 @@ int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *o
 int arx_tc2_head_prepare_weights(arx_handle *h, ArxTransformer &tr, cudaStream_t st);
 int arx_tc2_support_uc(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
 int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *uab, int64_t n_win, const int32_t *chosen,
-                        __half *y_img, int y_nk, cudaStream_t st);
+                        __half *y_img, int y_nk, int cls_stride, cudaStream_t st);
 int arx_tc_linear_f32_small(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table,
                             int T, cudaStream_t st);
 
 int arx_tc_build_wp_ext(arx_handle *h, const float *wp, const float *table, float *out, int N, int F, cudaStream_t st);
 
 int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, int g_ld, int g_voff, bool g_chunked, cudaStream_t st);
+                             float *partial, int g_ld, int g_voff, bool g_chunked, bool episodes, cudaStream_t st);
 // ---- persistent GEMM + tuple images (arx_gemm_p.cu)
 bool arx_tcp_supported(const ArxTcLinear &L);
 int arx_tcp_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,

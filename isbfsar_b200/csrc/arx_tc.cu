@@ -907,17 +907,20 @@ int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t
 }
 
 int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, cudaStream_t st) {
+                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, bool episodes,
+                     cudaStream_t st) {
   AttnParams p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img; p.G = G; p.Vq = Vq; p.partial = partial;
   p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.ldg = g_ld; p.voff = g_voff;
   p.trace = h->trace_buf;
   const bool mode0 = (h->T == 16 && tr.c == 2 && G != nullptr);
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_attention: generic epilogue needs Vq");
+  if (episodes && !(mode0 && arx_tc_slot_order(h, tr) && (variant & 128) == 0))
+    return arx_fail(h, ARX_ERR_INVALID, "tc_attention: episode mode needs the third-generation kernel");
   if (mode0 && arx_tc_slot_order(h, tr)) {
     // third-generation kernel by default; variant bit 7 (128) selects the second generation
     int rc = (variant & 128) ? arx_tc2_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, st)
-                             : arx_tc3_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, g_chunked, st);
+                             : arx_tc3_attention_launch(h, tr, kq_img, G, n_win, way, partial, g_ld, g_voff, g_chunked, episodes, st);
     if (rc) return rc;
     ARX_CUDA(h, arx_launch_pdl(k_finish_tc, dim3((unsigned)((n_win + 127) / 128)), dim3(128), 0, st, h->pdl, (const float *)partial, logits, chosen,
                                (int64_t)n_win, way, tr.N));
@@ -960,15 +963,14 @@ int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *
   if (!mode0 && !Vq) return arx_fail(h, ARX_ERR_INVALID, "tc_head: generic epilogue needs Vq");
   void (*kern)(const HeadParams) = nullptr;
   const bool slot = mode0 && arx_tc_slot_order(h, tr);
-  static bool rank_table_set = false;
-  if (slot && !rank_table_set) {
+  if (slot && !(h->dev_init & ARX_INIT_SLOT_RANK)) {
     short host[128];
     for (int q = 0; q < 128; ++q) {
       const int i = arx_slot_i(q), j = arx_slot_j(q);
       host[q] = (j == i) ? (short)-1 : (short)(i * (2 * 16 - i - 1) / 2 + (j - i - 1));
     }
     ARX_CUDA(h, cudaMemcpyToSymbol(c_slot_rank, host, sizeof(host)));
-    rank_table_set = true;
+    h->dev_init |= ARX_INIT_SLOT_RANK;
   }
   if (h->T == 16) kern = mode0 ? (slot ? k_head_tc<0, 16, true> : k_head_tc<0, 16, false>) : k_head_tc<1, 16, false>;
   else if (h->T == 32) kern = k_head_tc<1, 32, false>;

@@ -396,6 +396,7 @@ struct Head2Params {
   const int32_t *chosen;
   __half *y_img;           // fp16 activation image [ceil(n_win/128)][y_nk][128 x 64]
   int n_win, y_nk;
+  int cls_stride;          // episode mode: window b's classes start at b*cls_stride (0: one support set for all windows)
 };
 
 // per slot of the padded-triangular order: i | j << 8 | (lexicographic rank + 1) << 16 (0 = pad)
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
     if (warp == 0) {
       if (elect_one()) {            // producer: {Kq[b], Kc[c*]} then Uc[c*] per tile, two stages
         for (int f = 0; f < ntiles; ++f) {
-          const int b = blockIdx.x + f * gridDim.x, c = p.chosen[b], st = f & 1;
+          const int b = blockIdx.x + f * gridDim.x, c = p.chosen[b] + b * p.cls_stride, st = f & 1;
           const uint8_t *kq = reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)b * IMG_BYTES;
           const uint8_t *kc = reinterpret_cast<const uint8_t *>(p.kc_img) + (size_t)c * IMG_BYTES;
           mbar_wait(&bars[H2_EMPTY_KK + st], ((f >> 1) & 1) ^ 1);
@@ -659,9 +660,9 @@ int arx_tc2_support_uc(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t 
 }
 
 int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *uab, int64_t n_win, const int32_t *chosen,
-                        __half *y_img, int y_nk, cudaStream_t st) {
+                        __half *y_img, int y_nk, int cls_stride, cudaStream_t st) {
   Head2Params p{};
-  p.kq_img = kq_img; p.kc_img = tr.ks_img; p.uc_img = tr.uc_img; p.uab = uab; p.chosen = chosen; p.y_img = y_img; p.n_win = (int)n_win; p.y_nk = y_nk;
+  p.kq_img = kq_img; p.kc_img = tr.ks_img; p.uc_img = tr.uc_img; p.uab = uab; p.chosen = chosen; p.y_img = y_img; p.n_win = (int)n_win; p.y_nk = y_nk; p.cls_stride = cls_stride;
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
   { const int rc_ = arx_func_smem(h, k_head2_tc, (int)H2_SMEM_BYTES); if (rc_) return rc_; }
   ARX_CUDA(h, arx_launch_pdl(k_head2_tc, dim3(grid), dim3(NTHREADS2), H2_SMEM_BYTES, st, h->pdl, p));

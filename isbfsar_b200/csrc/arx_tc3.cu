@@ -38,6 +38,7 @@ struct Attn3Params {
   int n_win, way, ldg, voff;
   long long *trace;
   int stagger, token, gchunk;
+  int ep;      // episode mode (train.py:110-120 call shape): every window has its OWN `way` classes at class index window*way + c; groups hold one window
 };
 #define ARX_TRACE_TILES 64
 #define TRACE3(role, tile, k) do { if (p.trace && blockIdx.x == 0 && (tile) < ARX_TRACE_TILES) p.trace[(((role) * ARX_TRACE_TILES) + (tile)) * 8 + (k)] = clock64(); } while (0)
@@ -93,9 +94,10 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + B_COUNT * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this CTA's window groups: g = blockIdx.x, blockIdx.x + gridDim.x, ...; a group is 2 windows (the last may be 1)
-  const int n_groups = (p.n_win + 1) / 2;
+  const int GW = p.ep ? 1 : 2;                     // windows per group
+  const int n_groups = (p.n_win + GW - 1) / GW;
   const int my_groups = n_groups > (int)blockIdx.x ? (n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  auto group_nw = [&](int gi) { return min(2, p.n_win - ((int)blockIdx.x + gi * (int)gridDim.x) * 2); };
+  auto group_nw = [&](int gi) { return min(GW, p.n_win - ((int)blockIdx.x + gi * (int)gridDim.x) * GW); };
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[B_FULL_KQ], 1); mbar_init(&bars[B_EMPTY_KQ], 1);
@@ -122,9 +124,10 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
       if (elect_one()) {            // producer: class operands -- Kc single-buffered (one MMA1 per class), Vc^T in a 2-stage ring
         int k = 0;
         for (int gi = 0; gi < my_groups; ++gi) {
+          const size_t cbase = p.ep ? (size_t)(blockIdx.x + gi * gridDim.x) * p.way : 0;
           for (int c = 0; c < p.way; ++c, ++k) {
-            const uint8_t *kc = reinterpret_cast<const uint8_t *>(p.kc_img) + (size_t)c * IMG_BYTES;
-            const uint8_t *vc = reinterpret_cast<const uint8_t *>(p.vct_img) + (size_t)c * IMG_BYTES;
+            const uint8_t *kc = reinterpret_cast<const uint8_t *>(p.kc_img) + (cbase + c) * IMG_BYTES;
+            const uint8_t *vc = reinterpret_cast<const uint8_t *>(p.vct_img) + (cbase + c) * IMG_BYTES;
             mbar_wait(&bars[B_EMPTY_KC], (k & 1) ^ 1);
             mbar_arrive_expect_tx(&bars[B_FULL_KC], IMG_BYTES);
             bulk_g2s(smem + OFF_KC, kc, SUB_BYTES, &bars[B_FULL_KC]);
@@ -144,14 +147,14 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
           mbar_wait(&bars[B_EMPTY_KQ], (gi & 1) ^ 1);
           mbar_arrive_expect_tx(&bars[B_FULL_KQ], nw * IMG_BYTES);
           for (int w = 0; w < nw; ++w) {
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)(g * 2 + w) * IMG_BYTES;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)(g * GW + w) * IMG_BYTES;
             bulk_g2s(smem + OFF_KQ + w * SUB_BYTES, src, SUB_BYTES, &bars[B_FULL_KQ]);                              // d 0..63
             bulk_g2s(smem + OFF_KQ + 2 * SUB_BYTES + w * SUB_BYTES, src + SUB_BYTES, SUB_BYTES, &bars[B_FULL_KQ]);  // d 64..127
           }
           // Kq is single-buffered, so the next group's load is exposed at the group boundary: have it wait in L2, not in HBM
           if (gi + 1 < my_groups) {
             const int nwn = group_nw(gi + 1);
-            bulk_prefetch_l2(reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)((g + gridDim.x) * 2) * IMG_BYTES, nwn * IMG_BYTES);
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)((g + gridDim.x) * GW) * IMG_BYTES, nwn * IMG_BYTES);
           }
         }
       }
@@ -337,8 +340,8 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
             for (int m = 0; m < 8; ++m) bb[m] = pack2(__ldg(g0 + (size_t)(2 * m) * p.ldg + DD), __ldg(g0 + (size_t)(2 * m + 1) * p.ldg + DD));
           }
         };
-        load_ab(g * 2, a0, bb0);
-        if (nw > 1) load_ab(g * 2 + 1, a1, bb1);
+        load_ab(g * GW, a0, bb0);
+        if (nw > 1) load_ab(g * GW + 1, a1, bb1);
       }
       // one tile: window slot w (compile-time, so a/bb stay in registers) of class c
       auto tile = [&](auto wc, const float (&a)[16], const uint64_t (&bb)[8]) {
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
         float t = al + ah;
 #pragma unroll
         for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) p.partial[((size_t)(g * 2 + w) * p.way + c) * 4 + quad] = t;
+        if (lane == 0) p.partial[((size_t)(g * GW + w) * p.way + c) * 4 + quad] = t;
       };
       tile(std::integral_constant<int, 0>{}, a0, bb0);
       tile(std::integral_constant<int, 1>{}, a1, bb1);
@@ -381,14 +384,15 @@ __global__ void __launch_bounds__(NTHREADS3, 1) k_attn_tc3(const Attn3Params p) 
 }  // namespace
 
 int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, int g_ld, int g_voff, bool g_chunked, cudaStream_t st) {
+                             float *partial, int g_ld, int g_voff, bool g_chunked, bool episodes, cudaStream_t st) {
   Attn3Params p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img_bf; p.G = G; p.partial = partial;
   p.n_win = (int)n_win; p.way = way; p.ldg = g_ld; p.voff = g_voff; p.trace = h->trace_buf;
   p.gchunk = g_chunked ? 1 : 0;
+  p.ep = episodes ? 1 : 0;
   p.token = h->attn_stagger < 0;
   p.stagger = h->attn_stagger < 0 ? 0 : h->attn_stagger;
-  const int groups = (int)((n_win + 1) / 2);
+  const int groups = episodes ? (int)n_win : (int)((n_win + 1) / 2);
   const int grid = groups < h->sm_count ? groups : h->sm_count;
   auto kern = h->attn_poly == 0 ? k_attn_tc3<0> : (h->attn_poly == 2 ? k_attn_tc3<2> : (h->attn_poly == 4 ? k_attn_tc3<4> : k_attn_tc3<3>));
   { const int rc_ = arx_func_smem(h, kern, (int)SMEM_BYTES); if (rc_) return rc_; }

@@ -53,9 +53,15 @@ def broadcast_support(scorer, way: int, src: int = 0, group=None, device=None) -
     with torch.cuda.stream(comm):
         if rank == src:
             scorer.export_support(out=blob)
+            exported = torch.cuda.Event()
+            exported.record()
         dist.broadcast(blob, src=src, group=group)
         if rank != src:
             scorer.import_support(blob, way)
+    if rank == src:
+        # the next set_support (issued on the current stream) rewrites the tensors the export is reading: order it
+        # behind the export copy (not behind the collective)
+        torch.cuda.current_stream(device).wait_event(exported)
 
 
 def gather_scores(logits: torch.Tensor, is_true, n_total: int, group=None):

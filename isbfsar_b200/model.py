@@ -373,6 +373,28 @@ class TRXOS(nn.Module):
                                                  C.byref(t)), h, "arx_score_host_submit")
         return _HostTicket(self, int(t.value), q, logits, is_true)
 
+    def score_episodes(self, query, poses=None, features=None):
+        """Training / evaluation call shape (train.py:110-120, compute_fsos.py:89-98): episode i scores query i
+        (b,T,3J) against ITS OWN support classes, poses (b,W,T,3J) or features (b,W,T,F).  One batched pass
+        (arx_score_episodes); replaces the current support set.  -> logits (b,W), is_true (b,1) [None without DISC]."""
+        h = self._ensure()
+        dev = self._device()
+        lib = _lib.load()
+        q = self._f32c(query, dev)
+        sup = self._f32c(features if features is not None else poses, dev)
+        assert sup.dim() == 4 and sup.shape[0] == q.shape[0], "support must be (b,W,T,.) with the query's batch size"
+        b, way = q.shape[0], sup.shape[1]
+        logits = torch.empty((b, way), dtype=torch.float32, device=dev)
+        is_true = torch.empty((b, 1), dtype=torch.float32, device=dev) if self.model == "DISC" else None
+        if b == 0:
+            return logits, is_true
+        with torch.cuda.device(dev):
+            _lib.check(lib.arx_score_episodes(h, C.c_void_p(sup.data_ptr()), 1 if features is not None else 0, way,
+                                              C.c_void_p(q.data_ptr()), b, C.c_void_p(logits.data_ptr()),
+                                              C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None,
+                                              self._stream()), h, "arx_score_episodes")
+        return logits, is_true
+
     def score_features(self, ti, qfeats):
         """`transformers[ti](support, labels, queries)['logits']` from frame features (B,T,F)."""
         h = self._ensure()
@@ -464,14 +486,12 @@ class TRXOS(nn.Module):
             logits, is_true = self.score(q)
             feats_all = self._all_support_features(src, ss_features, dev)
         else:
-            lo, it = [], []
-            for i in range(b):
-                set_from(src[i])
-                l, t = self.score(q[i:i + 1])
-                lo.append(l)
-                it.append(t)
-            logits = torch.cat(lo)
-            is_true = torch.cat(it) if it[0] is not None else None
+            # every batch row is its own episode (train.py:110-120): all of them in one batched pass
+            sel = src.index_select(1, lab_t)                      # class order = ss_labels[0] (model.py:95-98)
+            if ss_features is not None:
+                logits, is_true = self.score_episodes(q, features=sel)
+            else:
+                logits, is_true = self.score_episodes(q, poses=sel)
             feats_all = self._all_support_features(src, ss_features, dev)
         out = {"logits": logits, "support_features": feats_all}
         if is_true is not None:

@@ -174,8 +174,20 @@ def decode_case(name):
     print(name, poses_ref.shape, "valid", valid.mean())
 
 
+def support_set_fixture():
+    """The reference's own saved support set (assets/saved/support_set.pkl + requires_focus.pkl, written by
+    main.py:321-326 `save`): copied byte for byte as the interchange fixture (a data asset, not source).  It is an
+    OrderedDict name -> {"poses": (16,90), "features": (16,256)} of CUDA tensors, exactly what `load` (main.py:328-333)
+    assigns to `ActionRecognizer.support_set`."""
+    import shutil
+    for src, dst in [("assets/saved/support_set.pkl", "ref_support_set.pkl"), ("assets/saved/requires_focus.pkl", "ref_requires_focus.pkl")]:
+        shutil.copyfile(os.path.join(REF, src), os.path.join(OUT, dst))
+    print("support-set fixture copied")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    support_set_fixture()
     from oracle.synth import Cfg
     trx_case("cfg1_w5_t16_structured", Cfg(), 64, 0, 1, "structured")
     trx_case("cfg1_w5_t16_iid", Cfg(), 64, 0, 3, "iid")

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.synth import Cfg, make_episode, make_state_dict, make_heatmaps
+from oracle.synth import Cfg, make_episode, make_state_dict, make_heatmaps  # noqa: F401
 from oracle.trx_oracle import TrxOracle
 from tests.util import Args, make_model, rel_err, torch_sd
 
@@ -454,3 +454,323 @@ def test_export_import_support_roundtrip():
     assert m2.last_path() == 2 and torch.equal(a, c) and torch.equal(b, d)
     with pytest.raises(RuntimeError):
         m2.support_features()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Round 2: the acceptance criteria at FULL size, ties, hooks, cache round trip, episodes, API races
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["structured", "iid"])
+def test_cfg2_all_4096_windows_against_oracle(kind):
+    """BASELINE cfg2 acceptance on EVERY window: logits / is_true within 1e-3 relative; identical argmax and identical
+    accept/reject on >= 99.9 % of the windows (structured inputs; iid inputs conditioned on the reference margin)."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, planted = make_episode(cfg, 4096, 41, kind)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query)
+    logits, is_true = logits.cpu().numpy(), is_true.cpu().numpy()
+    assert rel_err(logits, lo).max() < TOL_TC and rel_err(is_true, it).max() < TOL_TC
+    if kind == "structured":
+        assert (logits.argmax(1) == lo.argmax(1)).mean() >= 0.999
+    else:
+        srt = np.sort(lo, 1)
+        ok = (srt[:, -1] - srt[:, -2]) / np.abs(srt[:, -1]) > 2 * TOL_TC
+        assert ok.mean() > 0.5 and (logits.argmax(1)[ok] == lo.argmax(1)[ok]).all()
+    assert ((is_true > 0.5) == (it > 0.5)).mean() >= 0.999
+
+
+def test_cfg3_65536_windows_60way_1024_oracle_checked():
+    """BASELINE cfg3 at full size on one GPU: 60-way x 65 536 windows; 1024 windows spread over the batch meet the oracle."""
+    cfg = Cfg(way=60)
+    m, sd = make_model(cfg, 0)
+    B = 65536
+    support, labels, query, planted = make_episode(cfg, B, 61, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    assert m.last_path() == 2 and logits.shape == (B, 60)
+    assert (logits.argmax(1).cpu().numpy() == planted).all()
+    idx = np.r_[0:256, 20000:20256, 40001:40257, B - 256:B]
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query[idx], chunk=64)
+    assert rel_err(logits[idx].cpu(), lo).max() < TOL_TC and rel_err(is_true[idx].cpu(), it).max() < TOL_TC
+    assert np.array_equal(logits[idx].argmax(1).cpu().numpy(), lo.argmax(1))
+    assert np.array_equal((is_true[idx] > 0.5).cpu().numpy(), it > 0.5)
+
+
+def test_cfg4_t32_pairs_64_windows_against_oracle():
+    """BASELINE cfg4 (i): T=32, 20-way, pair tuples N=496 -> logits + is_true (discriminator fc1 = (256, 15 872))."""
+    cfg = Cfg(way=20, seq_len=32, temp_set=[2, 3])
+    m, sd = make_model(cfg, 0)
+    support, labels, query, planted = make_episode(cfg, 64, 5, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true = m.score(torch.from_numpy(query).cuda())
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query, chunk=16)
+    tol = tol_for(m)
+    assert rel_err(logits.cpu(), lo).max() < tol and rel_err(is_true.cpu(), it).max() < tol
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), lo.argmax(1)) and (lo.argmax(1) == planted).all()
+    assert np.array_equal((is_true > 0.5).cpu().numpy(), it > 0.5)
+
+
+@pytest.mark.parametrize("T,way,B", [(16, 5, 8), (32, 20, 2)])
+def test_triples_against_oracle(T, way, B):
+    """Cardinality-3 transformer (cfg4 (ii)) against the oracle's transformers[1] restatement at B >= 2."""
+    cfg = Cfg(way=way, seq_len=T, temp_set=[2, 3])
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, B, 9, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    qf = m.embed(torch.from_numpy(query).cuda())
+    logits = m.score_features(1, qf).cpu().numpy()
+    o = TrxOracle(cfg, sd)
+    with torch.no_grad():
+        ssf = o.embed(torch.from_numpy(support))
+        ref = o.cross_transformer(ssf.expand(B, -1, -1, -1), torch.from_numpy(labels).long(), o.embed(torch.from_numpy(query)).unsqueeze(1), ti=1)
+    assert rel_err(logits, ref["logits"].numpy()).max() < tol_for(m)
+    assert np.array_equal(logits.argmax(1), ref["logits"].numpy().argmax(1))
+
+
+def test_argmax_tie_takes_first_class():
+    """model.py:323: torch.argmax returns the FIRST maximal index -- two identical support classes tie exactly."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, planted = make_episode(cfg, 257, 13, "structured")
+    support[0, 3] = support[0, 1]                       # class 3 is a copy of class 1
+    query = (support[0, np.where(planted == 3, 1, planted)] + np.float32(0.05) * np.random.default_rng(3).standard_normal(query.shape)).astype(np.float32)
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    logits, is_true, chosen = m.score(torch.from_numpy(query).cuda(), want_chosen=True)
+    lg = logits.cpu().numpy()
+    assert np.array_equal(lg[:, 1], lg[:, 3])           # same operands, same arithmetic: bit-identical columns
+    ch = chosen.cpu().numpy()
+    assert np.array_equal(ch, lg.argmax(1))             # numpy argmax is first-max too
+    assert (ch != 3).all() and (ch[(planted == 1) | (planted == 3)] == 1).all()
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query)
+    assert np.array_equal(ch, lo.argmax(1))
+    assert rel_err(is_true.cpu(), it).max() < TOL_TC
+
+
+def test_add_hook_scores_match_oracle_probs():
+    """add_hook=True: transformers[0].scores gets one (b,1,N,N) softmax tensor per class (model.py:110-111), the
+    tensor visualize_heatmaps.py:123 reads; columns are normalised over the QUERY axis."""
+    from isbfsar_b200 import TRXOS
+    cfg = Cfg()
+    sd = make_state_dict(cfg, 0)
+    m = TRXOS(Args(cfg), add_hook=True)
+    m.load_state_dict(torch_sd(sd), strict=False)
+    m = m.cuda()
+    support, labels, query, _ = make_episode(cfg, 3, 17, "structured")
+    out = m({"sk": torch.from_numpy(support).cuda()}, torch.from_numpy(labels).cuda(), {"sk": torch.from_numpy(query).cuda()})
+    scores = m.transformers[0].scores
+    assert len(scores) == 5 and scores[0].shape == (3, 1, 120, 120)
+    ref = TrxOracle(cfg, sd).forward({"sk": np.repeat(support, 3, 0)}, labels, {"sk": query}, want=("probs",))
+    for c in range(5):
+        got = scores[c].cpu().numpy()
+        np.testing.assert_allclose(got, ref["probs"][c].numpy(), rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(got.sum(axis=-2), 1.0, rtol=1e-5)
+    true_index = 2                                       # the consumer's indexing (visualize_heatmaps.py:123)
+    assert scores[true_index][0][0].shape == (120, 120)
+    m({"sk": torch.from_numpy(support).cuda()}, torch.from_numpy(labels).cuda(), {"sk": torch.from_numpy(query).cuda()})
+    assert len(m.transformers[0].scores) == 10           # the hook appends on every forward, like the reference
+
+
+def test_support_cache_round_trip_is_stable():
+    """ar.py:56-74: a support set scored from poses caches its features; after the set changes, the cached classes
+    re-enter through the features path.  Both routes must give the same logits within the tolerance."""
+    from isbfsar_b200 import ActionRecognizer
+    cfg = Cfg()
+    sd = make_state_dict(cfg, 0)
+    ar = ActionRecognizer(Args(cfg), state_dict=torch_sd(sd))
+    rng = np.random.default_rng(23)
+    poses = (0.17 * rng.standard_normal((3, 16, 90))).astype(np.float32)
+    frames = (poses[1] + 0.05 * rng.standard_normal((16, 90))).astype(np.float32)
+    for i, n in enumerate(["a", "b"]):
+        ar.train({"flag": n, "data": {"poses": poses[i]}, "requires_focus": False})
+    for f in frames:
+        res1, os1, _ = ar.inference({"sk": f})              # poses route (no class has features yet)
+    assert all("features" in v for v in ar.support_set.values())
+    res2, os2, _ = ar.inference({"sk": frames[-1]})          # same window again: nothing changed, operands reused
+    ar.previous_frames = ar.previous_frames[:-1]
+    ar._support_key = None                                   # force the cached-features route for the same classes
+    res3, os3, _ = ar.inference({"sk": frames[-1]})
+    for k in res1:
+        assert abs(res3[k] / res1[k] - 1) < 1e-3
+    assert abs(os3[0] / os1[0] - 1) < 1e-3
+    # oracle on the same call sequence
+    oa = __import__("oracle.trx_oracle", fromlist=["ActionRecognizerOracle"]).ActionRecognizerOracle(cfg, sd)
+    for i, n in enumerate(["a", "b"]):
+        oa.train({"flag": n, "data": {"poses": poses[i]}, "requires_focus": False})
+    for f in frames:
+        ro, oo, _ = oa.inference({"sk": f})
+    for k in ro:
+        assert abs(res1[k] / ro[k] - 1) < 2e-3 and abs(res3[k] / ro[k] - 1) < 2e-3
+    # a third class arrives without features: the whole set goes back through the poses route (ar.py:62-67)
+    ar.train({"flag": "c", "data": {"poses": poses[2]}, "requires_focus": False})
+    oa.train({"flag": "c", "data": {"poses": poses[2]}, "requires_focus": False})
+    r4, _, _ = ar.inference({"sk": frames[-1]})
+    ro4, _, _ = oa.inference({"sk": frames[-1]})
+    assert list(r4) == ["a", "b", "c"]
+    for k in r4:
+        assert abs(r4[k] / ro4[k] - 1) < 2e-3
+    # in-place edit of a stored tensor must not leave stale operands on the device (ADVICE r1)
+    ar.support_set["a"]["poses"].copy_(torch.from_numpy(poses[2]).cuda())
+    ar.support_set["a"].pop("features")
+    oa.support_set["a"]["poses"] = torch.from_numpy(poses[2])
+    oa.support_set["a"].pop("features")
+    r5, _, _ = ar.inference({"sk": frames[-1]})
+    ro5, _, _ = oa.inference({"sk": frames[-1]})
+    for k in r5:
+        assert abs(r5[k] / ro5[k] - 1) < 2e-3
+
+
+@pytest.mark.parametrize("b", [1, 28, 300])
+def test_batched_episodes_match_oracle(b):
+    """train.py:110-120 / compute_fsos.py:89-98 call shape: every batch row has its own 5-way support set; all rows
+    go through ONE batched pass (arx_score_episodes)."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    o = TrxOracle(cfg, sd)
+    rng = np.random.default_rng(5 + b)
+    support = (0.17 * rng.standard_normal((b, 5, 16, 90))).astype(np.float32)
+    query = (support[np.arange(b), rng.integers(0, 5, b)] + 0.05 * rng.standard_normal((b, 16, 90))).astype(np.float32)
+    labels = np.tile(np.arange(5, dtype=np.int32), (b, 1))
+    l0 = m.launch_count()
+    out = m({"sk": torch.from_numpy(support).cuda()}, torch.from_numpy(labels).cuda(), {"sk": torch.from_numpy(query).cuda()})
+    assert m.launch_count() - l0 < 60 * (1 + b // 256)         # batched: launches do not grow with b
+    ref = o.forward({"sk": support}, labels, {"sk": query})
+    assert rel_err(out["logits"].cpu(), ref["logits"]).max() < TOL_TC
+    assert rel_err(out["is_true"].cpu(), ref["is_true"]).max() < TOL_TC
+    assert np.array_equal(out["logits"].argmax(1).cpu().numpy(), ref["logits"].numpy().argmax(1))
+    # features route
+    ssf = o.embed(torch.from_numpy(support))
+    out2 = m(None, torch.from_numpy(labels).cuda(), {"sk": torch.from_numpy(query).cuda()}, ss_features=ssf.cuda())
+    assert rel_err(out2["logits"].cpu(), ref["logits"]).max() < TOL_TC
+    # the pool replaced the support set: an ordinary score afterwards needs set_support again and is unaffected
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    lg, _ = m.score(torch.from_numpy(query[:4]).cuda())
+    lo, _ = o.score(support[:1], labels[:1], query[:4])
+    assert rel_err(lg.cpu(), lo).max() < TOL_TC
+
+
+def test_episodes_on_shapes_without_batched_kernels():
+    """T=8 has no batched-episode kernels: arx_score_episodes falls back to one episode at a time, same results."""
+    cfg = Cfg(seq_len=8)
+    m, sd = make_model(cfg, 0)
+    o = TrxOracle(cfg, sd)
+    rng = np.random.default_rng(2)
+    support = (0.17 * rng.standard_normal((5, 5, 8, 90))).astype(np.float32)
+    query = (support[np.arange(5), rng.integers(0, 5, 5)] + 0.05 * rng.standard_normal((5, 8, 90))).astype(np.float32)
+    labels = np.tile(np.arange(5, dtype=np.int32), (5, 1))
+    lg, it = m.score_episodes(torch.from_numpy(query).cuda(), poses=torch.from_numpy(support).cuda())
+    ref = o.forward({"sk": support}, labels, {"sk": query})
+    assert rel_err(lg.cpu(), ref["logits"]).max() < TOL_TC and rel_err(it.cpu(), ref["is_true"]).max() < TOL_TC
+
+
+def test_fsos_evaluation_driver_matches_oracle():
+    """compute_fsos.py:74-143 over synthetic loader-shaped episodes: identical FS / OS / FSOS accuracies from the
+    oracle and from the CUDA path (decisions agree on every episode)."""
+    from isbfsar_b200.eval import evaluate_fsos, synthetic_fsos_episodes
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    o = TrxOracle(cfg, sd)
+    kw = dict(n_batches=4, batch=28, way=5, seed=3)
+    got = evaluate_fsos(m, synthetic_fsos_episodes(**kw), 5, device="cuda")
+    ref = evaluate_fsos(lambda s, l, q: o.forward(s, l, q), synthetic_fsos_episodes(**kw), 5)
+    assert got == ref and got["episodes"] == 112
+    assert got["FS-ACC"] == 1.0                               # a noisy copy of an exemplar is recognised
+    assert 0.0 <= got["FSOS-ACC"] <= 1.0 and 0.0 <= got["OS-ACC"] <= 1.0
+
+
+def test_reference_support_set_pickle_interchange(golden_dir):
+    """main.py:321-333: the GUI saves/loads `ar.support_set` (an OrderedDict of CUDA tensors) with pickle.  The
+    reference's own saved file must drop into ActionRecognizer and behave like the reference logic on it."""
+    import pickle
+    from isbfsar_b200 import ActionRecognizer
+    from oracle.trx_oracle import ActionRecognizerOracle
+    cfg = Cfg()
+    sd = make_state_dict(cfg, 0)
+    ar = ActionRecognizer(Args(cfg), state_dict=torch_sd(sd))
+    with open(os.path.join(golden_dir, "ref_support_set.pkl"), "rb") as f:
+        ar.support_set = pickle.load(f)                      # main.py:329-330
+    with open(os.path.join(golden_dir, "ref_requires_focus.pkl"), "rb") as f:
+        ar.requires_focus = pickle.load(f)
+    assert list(ar.support_set) == ["hello", "get", "lift"] and ar.support_set["get"]["poses"].is_cuda
+    oa = ActionRecognizerOracle(cfg, sd)
+    for k, v in ar.support_set.items():
+        oa.support_set[k] = {kk: vv.detach().cpu().clone() for kk, vv in v.items()}
+    oa.requires_focus = dict(ar.requires_focus)
+    frames = (ar.support_set["get"]["poses"].cpu().numpy() + 0.02 * np.random.default_rng(1).standard_normal((16, 90))).astype(np.float32)
+    for f in frames:
+        res, os_, rf = ar.inference({"sk": f})
+        ro, oo, _ = oa.inference({"sk": f})
+    assert list(res) == ["hello", "get", "lift"] and rf == {"hello": True, "get": True, "lift": False}
+    for k in res:                                            # the file carries cached features: features route (ar.py:56-61)
+        assert abs(res[k] / ro[k] - 1) < 2e-3
+    assert abs(os_[0] / oo[0] - 1) < 1e-3
+    # drop the cached features: the poses route on the real recorded skeletons
+    for v in ar.support_set.values():
+        v.pop("features")
+    for v in oa.support_set.values():
+        v.pop("features")
+    res2, os2, _ = ar.inference({"sk": frames[-1]})
+    ro2, oo2, _ = oa.inference({"sk": frames[-1]})
+    for k in res2:
+        assert abs(res2[k] / ro2[k] - 1) < 2e-3
+    assert max(res2, key=res2.get) == max(ro2, key=ro2.get)
+    # save -> load round trip (main.py:321-333)
+    blob = pickle.dumps(ar.support_set)
+    ar.support_set = pickle.loads(blob)
+    res3, _, _ = ar.inference({"sk": frames[-1]})
+    ar.previous_frames = ar.previous_frames[:-1]
+    assert all(abs(res3[k] / res2[k] - 1) < 1e-3 for k in res2)
+
+
+def test_host_wait_on_old_tickets_and_two_caller_streams():
+    """waiting on the OLDEST of several in-flight tickets must block until its copies have landed; ticket
+    ids stay valid across a staging reallocation; scoring calls on two caller streams do not race on the workspace."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 4096, 121, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    ref, _ = m.score(torch.from_numpy(query).cuda())
+    ref = ref.cpu()
+    q = torch.from_numpy(query).pin_memory()
+    for _ in range(2):                                      # sized once: no reallocation (and no device-wide sync) below
+        m.score_host_async(q).result()
+    tickets = [m.score_host_async(q) for _ in range(5)]
+    lo, _ = tickets[0].result()                             # slot already reused twice
+    assert torch.equal(lo, ref)
+    for t in tickets[1:]:
+        assert torch.equal(t.result()[0], ref)
+    small = m.score_host_async(q[:100])
+    big = m.score_host_async(torch.cat([q, q]).pin_memory())   # larger request: staging reallocated
+    assert torch.equal(small.result()[0], ref[:100])
+    assert torch.equal(big.result()[0], torch.cat([ref, ref]))
+    # two caller streams, same handle
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    Q1, Q2 = torch.from_numpy(query[:2048]).cuda(), torch.from_numpy(query[2048:]).cuda()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            a = m.score(Q1)[0]
+        with torch.cuda.stream(s2):
+            b = m.score(Q2)[0]
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a.cpu(), ref[:2048]) and torch.equal(b.cpu(), ref[2048:])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_same_process():
+    """per-device one-time initialisation (__constant__ slot tables, function attributes) is per handle."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    support, labels, query, _ = make_episode(cfg, 300, 131, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    a, b = m.score(torch.from_numpy(query).cuda())
+    m2, _ = make_model(cfg, 0)
+    m2 = m2.to("cuda:1")
+    with torch.cuda.device(1):
+        m2.set_support(poses=torch.from_numpy(support[0]).to("cuda:1"))
+        c, d = m2.score(torch.from_numpy(query).to("cuda:1"))
+    assert torch.equal(a.cpu(), c.cpu()) and torch.equal(b.cpu(), d.cpu())
