@@ -183,7 +183,8 @@ ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t
  *         4 fp32 CUDA-core linear layers, 8 first-generation attention kernel, 16 unfused projection (row-major
  *         projections + k_prep_k_img), 32 first-generation head pass, 64 timing only: skip the tuple build,
  *         128 second-generation attention kernel, 512 tuple build inside the projection GEMM epilogue,
- *         1024 one-tile-per-CTA GEMMs for the frame MLP, 2048 head projection on the caller's stream.
+ *         1024 one-tile-per-CTA GEMMs for the frame MLP, 2048 head projection on the caller's stream,
+ *         4096 T=16 pair tuples on the tiled any-N kernels (set BEFORE the support set: it selects the operands built).
  *  key 1: (value != 0) arm a timeline trace of CTA 0 of the attention kernel.
  *  key 2: programmatic dependent launch for the score kernel chain.
  *  key 3: softmax-group scheduling of the attention kernel: < 0 the groups take turns on the MUFU phase
@@ -199,7 +200,8 @@ ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
 ARX_API int arx_debug_read_trace(arx_handle *h, long long *host_out);
 
 /* Introspection for tests/bench: kernel launches issued by this handle so far,
- * and which attention path the last arx_score used (1 = fp32, 2 = tcgen05). */
+ * and which attention path the last arx_score used: 1 = fp32 CUDA-core kernels, 2 = tcgen05 pipeline of the
+ * metric shape (T=16 pair tuples), 3 = tiled any-N tcgen05 kernels (T=32, triples, other T, ROWMAX variant). */
 ARX_API int64_t arx_launch_count(const arx_handle *h);
 ARX_API int arx_last_path(const arx_handle *h);
 

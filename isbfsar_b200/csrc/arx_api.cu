@@ -77,8 +77,10 @@ void free_support(arx_handle *h) {
   for (int i = 0; i < h->cfg.n_transformers; ++i) {
     cudaFree(h->tr[i].ks); cudaFree(h->tr[i].vs);
     cudaFree(h->tr[i].ks_img); cudaFree(h->tr[i].vs_img); cudaFree(h->tr[i].vs_img_bf); cudaFree(h->tr[i].uc_img);
+    cudaFree(h->tr[i].kc_tiles); cudaFree(h->tr[i].vct_tiles); cudaFree(h->tr[i].uc_tiles);
     h->tr[i].ks = h->tr[i].vs = nullptr;
     h->tr[i].ks_img = h->tr[i].vs_img = h->tr[i].vs_img_bf = h->tr[i].uc_img = nullptr;
+    h->tr[i].kc_tiles = h->tr[i].vct_tiles = h->tr[i].uc_tiles = nullptr;
   }
   cudaFree(h->ss_feat);
   cudaFree(h->ss_poses);
@@ -225,6 +227,7 @@ void arx_destroy(arx_handle *h) {
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     ArxTransformer &tr = h->tr[i];
     cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots); cudaFree(tr.bp_sums); cudaFree(tr.wp_ext);
+    cudaFree(tr.tup_packed);
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
@@ -250,6 +253,8 @@ void arx_destroy(arx_handle *h) {
   if (h->ev_support_done) cudaEventDestroy(h->ev_support_done);
   if (h->ev_score_done) cudaEventDestroy(h->ev_score_done);
   cudaFree(h->ws);
+  cudaFree(h->zscratch);
+  cudaFree(h->tcn_diag);
   cudaFree(h->ss_scratch);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
@@ -372,6 +377,31 @@ int arx_embed(arx_handle *h, const float *frames_dev, int64_t n_frames, float *f
   return ARX_OK;
 }
 
+// ---- stream-capture awareness -------------------------------------------------------------------------------------
+// A caller may capture whole steps (set_support + score + its own collectives) into ONE CUDA graph.  Inside a capture a
+// stream may only wait on events recorded in the SAME capture, so every internal event remembers the capture it was
+// recorded in (0 = recorded eagerly) and waits follow these rules:
+//   same context (both eager, or same capture)      -> cudaStreamWaitEvent
+//   capturing now, event recorded eagerly before     -> the host waits for the event (cudaEventQuery poll: legal during
+//                                                       capture), the graph itself needs no dependency
+//   otherwise (event belongs to another capture)     -> nothing to wait for: replays are ordered by the launching stream
+static unsigned long long capture_id(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo(st, &cs, &id) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return cs == cudaStreamCaptureStatusActive ? (id ? id : 1ull) : 0ull;
+}
+static int wait_event_cap(arx_handle *h, cudaStream_t waiter, cudaEvent_t ev, unsigned long long ev_cid, unsigned long long cur_cid) {
+  if (ev_cid == cur_cid) {
+    ARX_CUDA(h, cudaStreamWaitEvent(waiter, ev, 0));
+  } else if (cur_cid != 0 && ev_cid == 0) {
+    cudaError_t e;
+    while ((e = cudaEventQuery(ev)) == cudaErrorNotReady) {}
+    if (e != cudaSuccess) return arx_fail(h, ARX_ERR_CUDA, "event query failed: %s", cudaGetErrorString(e));
+  }
+  return ARX_OK;
+}
+
 // fork the support chain onto the side stream (after everything already queued on the caller's stream and after
 // the last scoring pass that still reads the current operands)
 static int support_fork(arx_handle *h, cudaStream_t st, cudaStream_t *side) {
@@ -381,9 +411,15 @@ static int support_fork(arx_handle *h, cudaStream_t st, cudaStream_t *side) {
     ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_support_done, cudaEventDisableTiming));
     if (!h->ev_score_done) ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
   }
+  const unsigned long long cid = capture_id(st);
   ARX_CUDA(h, cudaEventRecord(h->ev_fork, st));
   ARX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-  if (h->score_recorded) ARX_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_score_done, 0));
+  // the last scoring pass still reads the current operands: on `st` itself it is already ordered before the fork
+  if (h->score_recorded && h->last_score_stream != st) {
+    const int rc = wait_event_cap(h, h->side_stream, h->ev_score_done, h->score_cid, cid);
+    if (rc) return rc;
+  }
+  h->support_cid = cid;
   *side = h->side_stream;
   return ARX_OK;
 }
@@ -394,7 +430,23 @@ static int support_join_record(arx_handle *h) {
 }
 // consumers of the support operands on stream st
 static int support_wait(arx_handle *h, cudaStream_t st) {
-  if (h->support_recorded) ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_support_done, 0));
+  if (h->support_recorded) return wait_event_cap(h, st, h->ev_support_done, h->support_cid, capture_id(st));
+  return ARX_OK;
+}
+static int score_done_record(arx_handle *h, cudaStream_t st) {
+  if (!h->ev_score_done) ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
+  ARX_CUDA(h, cudaEventRecord(h->ev_score_done, st));
+  h->score_recorded = true;
+  h->last_score_stream = st;
+  h->score_cid = capture_id(st);
+  return ARX_OK;
+}
+// the shared workspace may still be in use by streamed host requests or by a scoring pass on another stream
+static int workspace_wait(arx_handle *h, cudaStream_t st) {
+  const unsigned long long cid = capture_id(st);
+  int rc;
+  if (st != h->hs_comp && h->hs_submitted > 0 && (rc = wait_event_cap(h, st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0, cid))) return rc;
+  if (h->score_recorded && h->last_score_stream != st && (rc = wait_event_cap(h, st, h->ev_score_done, h->score_cid, cid))) return rc;
   return ARX_OK;
 }
 
@@ -443,6 +495,28 @@ static int support_scratch_reserve(arx_handle *h, int way, SupportScratch *out) 
   return ARX_OK;
 }
 
+// Which kernels score transformer `tr`:  the T=16 pair pipeline (arx_tc3.cu and friends: fused tuple images, head by
+// linearity, graph replay), the tiled any-N tcgen05 kernels (arx_tcn.cu: T=32, triples, other T, LayerNorm affines
+// outside the static exp2 bound), or the fp32 CUDA-core kernels (forced, debug outputs, D != 128).
+static bool route_gen3(const arx_handle *h, const ArxTransformer &tr) {
+  return h->cfg.force_path != 1 && arx_tc_supported(h, tr) && h->T == 16 && tr.c == 2 && h->tc_linears && (h->tc_variant & 4096) == 0;
+}
+// LayerNorm affines outside the static bound: the ROWMAX variant of the tiled kernels is overflow-safe, but the fp16
+// operands of QK^T are no longer accurate enough there (measured on B200: gamma = 3 gives 5e-3 relative logit error
+// against the stated 1e-3; the error grows with gamma^2 like the bound does).  Parity first: such weights score on the
+// fp32 kernels unless the caller forces the tensor-core path (force_path = 2), and the handle says so once on stderr.
+static bool route_tiled(const arx_handle *h, const ArxTransformer &tr) {
+  return h->cfg.force_path != 1 && !route_gen3(h, tr) && arx_tcn_supported(h, tr) && (!arx_tcn_needs_rowmax(tr) || h->cfg.force_path == 2);
+}
+static void warn_fp32_fallback(arx_handle *h, int ti) {
+  const ArxTransformer &tr = h->tr[ti];
+  if (h->cfg.force_path == 1 || (h->warned & (1u << ti)) || !arx_tcn_supported(h, tr) || !arx_tcn_needs_rowmax(tr)) return;
+  h->warned |= 1u << ti;
+  fprintf(stderr, "libarx: transformers[%d].norm_k has a LayerNorm affine outside the fp16 tensor-core bound (|S| <= %.0f > %.0f): scoring on the "
+                  "fp32 CUDA-core kernels (about 30x slower) to stay within the 1e-3 tolerance; force_path=2 selects the tensor-core "
+                  "row-max variant at reduced accuracy\n", ti, (double)tr.softmax_bound, 100.0 / ARX_SOFTMAX_LOG2E);
+}
+
 // projection + tuple/LayerNorm/image build of the support set from frame features given as an fp16 image
 // (tensor-core path) or as fp32 rows (general path)
 static int support_from_features(arx_handle *h, const __half *f_img, const float *feats32, int way, float *G, cudaStream_t st) {
@@ -456,10 +530,11 @@ static int support_from_features(arx_handle *h, const __half *f_img, const float
     } else {
       if ((rc = project_frames(h, tr, feats32, rows, G, st))) return rc;
     }
-    const bool imgs = h->cfg.force_path != 1 && arx_tc_supported(h, tr);
+    const bool imgs = route_gen3(h, tr);
     if (h->D == 128) {
       if ((rc = arx_tc_support_build(h, tr, G, way, imgs, st))) return rc;      // tuples + LayerNorm + operand images, one launch
       if (imgs && i == 0 && h->tc_linears && h->cfg.has_discriminator && h->T == 16 && tr.c == 2 && (rc = arx_tc2_support_uc(h, tr, way, st))) return rc;
+      if (route_tiled(h, tr) && (rc = arx_tcn_prep_support(h, tr, way, i == 0 && h->cfg.has_discriminator && tr.c == 2 && h->T <= 32, st))) return rc;
     } else {
       if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
     }
@@ -596,9 +671,11 @@ int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *s
     p += n;
     ARX_CUDA(h, cudaMemcpyAsync(tr.vs, p, n * sizeof(float), cudaMemcpyDeviceToDevice, ss));
     p += n;
-    if (h->cfg.force_path != 1 && arx_tc_supported(h, tr)) {
+    if (route_gen3(h, tr)) {
       if ((rc = arx_tc_prep_support(h, tr, way, ss))) return rc;
       if (i == 0 && h->tc_linears && h->cfg.has_discriminator && h->T == 16 && tr.c == 2 && (rc = arx_tc2_support_uc(h, tr, way, ss))) return rc;
+    } else if (route_tiled(h, tr)) {
+      if ((rc = arx_tcn_prep_support(h, tr, way, i == 0 && h->cfg.has_discriminator && tr.c == 2 && h->T <= 32, ss))) return rc;
     }
   }
   h->way = way;
@@ -672,6 +749,106 @@ template <class F> static int score_segment(arx_handle *h, ArxScoreGraph *g, int
 }
 }  // extern "C++"
 
+// ---- scoring on the tiled any-N tcgen05 kernels (arx_tcn.cu) -----------------------------------------------------
+struct TcnWs {
+  __half *x_img, *h_img, *f_img, *kq, *y_img, *h1_img;
+  float *H1, *FE, *G, *partial, *uab, *y, *h1, *h2;
+  size_t bytes;
+};
+static TcnWs carve_tcn(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, bool tcl, void *base) {
+  Carver c(base);
+  TcnWs w{};
+  const int64_t rows = n * h->T, rows_pad = (rows + 127) / 128 * 128, n_pad = (n + 127) / 128 * 128;
+  const int nq = tr.Npad / 128;
+  w.x_img = (tcl && from_frames) ? c.take<__half>(rows_pad * 128) : nullptr;
+  w.h_img = (tcl && from_frames) ? c.take<__half>(rows_pad * 192) : nullptr;
+  w.f_img = tcl ? c.take<__half>(rows_pad * 320) : nullptr;
+  w.H1 = (!tcl && from_frames) ? c.take<float>(rows * h->H) : nullptr;
+  w.FE = (!tcl && from_frames) ? c.take<float>(rows * h->F) : nullptr;
+  w.G = c.take<float>(rows_pad * 2 * tr.c * h->D);
+  w.kq = c.take<__half>((size_t)n * nq * 128 * 128);
+  w.partial = c.take<float>(n * way * 4);
+  if (disc) {
+    const int64_t K1 = (int64_t)tr.N * h->T;
+    w.uab = c.take<float>(rows * 64 + 256);
+    if (tcl) {
+      w.y_img = c.take<__half>(n_pad * (int64_t)h->tl_d1.nk * 64);
+      w.h1_img = c.take<__half>(n_pad * 256);
+    } else {
+      w.y = c.take<float>(n * K1);
+      w.h1 = c.take<float>(n * 256);
+      w.h2 = c.take<float>(n * 64);
+    }
+  }
+  w.bytes = c.off + 256;
+  return w;
+}
+
+static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
+                     float *is_true_dev, int32_t *chosen_dev, cudaStream_t st) {
+  const ArxTransformer &tr = h->tr[ti];
+  const bool from_frames = query_dev != nullptr, disc = is_true_dev != nullptr, tcl = h->tc_linears && (h->tc_variant & 4) == 0;
+  const int way = h->way;
+  if (!tr.kc_tiles) return arx_fail(h, ARX_ERR_STATE, "score: support operands of the tiled kernels are missing (set the support set again)");
+  if (disc && !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "score: the open-set head of the tiled kernels needs pair tuples and T <= 32");
+  // windows per pass: workspace budget (the query tiles are 32 KB per 128 tuples per window)
+  const size_t per = carve_tcn(h, tr, 128, way, from_frames, disc, tcl, nullptr).bytes / 128 + 1;
+  int64_t chunk = h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096;
+  chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(chunk, (int64_t)(((size_t)3 << 30) / per)), n_windows));
+  const size_t need = carve_tcn(h, tr, chunk, way, from_frames, disc, tcl, nullptr).bytes + (chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256);
+  int rc = arx_ws_reserve(h, need);
+  if (rc) return rc;
+  TcnWs w = carve_tcn(h, tr, chunk, way, from_frames, disc, tcl, h->ws);
+  int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + need - (size_t)chunk * sizeof(int32_t) - 256);
+  const int ldg = 2 * tr.c * h->D;
+  h->last_path = 3;
+  for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
+    const int64_t n = std::min(chunk, n_windows - b0), rows = n * h->T;
+    if ((rc = prof_mark(h, 0, st))) return rc;
+    const float *FE = nullptr;
+    if (tcl) {
+      const int f_nk = tr.tl_proj.nk, f_onehot = tr.table_in_gemm ? f_nk - 1 : -1;
+      if (from_frames) {
+        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
+      } else if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, f_nk, f_onehot, st))) return rc;
+      if ((rc = prof_mark(h, 1, st))) return rc;
+      if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, ldg, tr.table_in_gemm ? nullptr : tr.bp, h->T, st))) return rc;
+    } else {
+      if (from_frames) {
+        if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, rows, w.H1, w.FE, st))) return rc;
+        FE = w.FE;
+      } else FE = qfeats_dev + b0 * h->T * h->F;
+      if ((rc = prof_mark(h, 1, st))) return rc;
+      if ((rc = project_frames(h, tr, FE, rows, w.G, st))) return rc;
+    }
+    if ((rc = prof_mark(h, 2, st))) return rc;
+    if ((rc = support_wait(h, st))) return rc;          // tup_packed and the class tiles come from the support chain
+    if ((rc = arx_tcn_prep_query(h, tr, w.G, ldg, n, w.kq, st))) return rc;
+    if ((rc = prof_mark(h, 3, st))) return rc;
+    int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
+    if ((rc = arx_tcn_attention(h, tr, w.kq, w.G, ldg, n, way, w.partial, logits_dev + b0 * way, ch, st))) return rc;
+    if ((rc = prof_mark(h, 4, st))) return rc;
+    if (disc) {
+      if (tcl && ((int64_t)tr.N * h->T) % 64)       // fc1's K is padded to whole 64-column sub-tiles: the pad columns must be zero, not stale
+        ARX_CUDA(h, cudaMemsetAsync(w.y_img, 0, (size_t)((n + 127) / 128 * 128) * h->tl_d1.nk * 64 * sizeof(__half), st));
+      if ((rc = arx_tcn_head(h, tr, w.kq, w.G, ldg, n, ch, w.uab, w.y, w.y_img, tcl ? h->tl_d1.nk : 0, st))) return rc;
+      if (tcl) {
+        if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true_dev + b0, st))) return rc;
+      } else {
+        const int K1 = tr.N * h->T;
+        if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+        if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+        if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
+      }
+    }
+    if ((rc = prof_mark(h, 5, st))) return rc;
+  }
+  return ARX_OK;
+}
+
 #define ARX_EP_UNSUPPORTED (-100)   /* internal: episode mode asked for a shape the batched kernels do not cover */
 // ep_way > 0: episode mode -- window b is scored against classes [b*ep_way, (b+1)*ep_way) of the support pool
 static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
@@ -687,7 +864,15 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   const int way = ep_way > 0 ? ep_way : h->way;
   if (ep_way > 0 && (int64_t)ep_way * n_windows != h->way) return arx_fail(h, ARX_ERR_STATE, "score: episode pool does not match the batch");
   const bool debug_out = probs || protos;
-  bool use_tc = h->cfg.force_path != 1 && !debug_out && arx_tc_supported(h, tr) && tr.ks_img != nullptr;
+  if (ep_way == 0 && !debug_out && route_tiled(h, tr)) {
+    int rc_t = workspace_wait(h, st);
+    if (rc_t) return rc_t;
+    if ((rc_t = score_tcn(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st))) return rc_t;
+    return score_done_record(h, st);
+  }
+  if (ep_way > 0 && !route_gen3(h, tr)) return ARX_EP_UNSUPPORTED;
+  if (!debug_out && !route_gen3(h, tr)) warn_fp32_fallback(h, ti);
+  bool use_tc = !debug_out && route_gen3(h, tr) && tr.ks_img != nullptr;
   if (h->cfg.force_path == 2 && !use_tc && !debug_out)
     return arx_fail(h, ARX_ERR_INVALID, "score: force_path=2 but the tcgen05 path does not support this shape (N=%d, bound=%g)", tr.N,
                     (double)tr.softmax_bound);
@@ -714,10 +899,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, use_tc, tuples32, tcl, tc_head);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
   h->last_path = use_tc ? 2 : 1;
-  if (st != h->hs_comp && h->hs_submitted > 0)      // the shared workspace may still be in use by streamed requests
-    ARX_CUDA(h, cudaStreamWaitEvent(st, h->hs_ev_comp[(h->hs_submitted - 1) % ARX_HOST_DEPTH], 0));
-  // ... or by a scoring pass enqueued on ANOTHER stream (one workspace per handle): order this pass behind it
-  if (h->score_recorded && h->last_score_stream != st) ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_score_done, 0));
+  if ((rc = workspace_wait(h, st))) return rc;
   bool aux_pending = false;
   ArxScoreGraph *sg = nullptr;
   bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;     // the default streams cannot be captured
@@ -840,11 +1022,7 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
     if ((rc = prof_mark(h, 5, st))) return rc;
   }
   if (sg) sg->seen++;
-  if (!h->ev_score_done) ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_score_done, cudaEventDisableTiming));
-  ARX_CUDA(h, cudaEventRecord(h->ev_score_done, st));
-  h->score_recorded = true;
-  h->last_score_stream = st;
-  return ARX_OK;
+  return score_done_record(h, st);
 }
 
 int arx_score(arx_handle *h, const float *query_dev, int64_t n_windows, float *logits_dev, float *is_true_dev, int32_t *chosen_dev,
@@ -1001,7 +1179,6 @@ int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_wind
   ARX_CUDA(h, cudaEventRecord(h->hs_ev_h2d[s], h->hs_h2d));
   // scoring: after its inputs arrived and after the results previously held in this slot went back to the host
   ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_h2d[s], 0));
-  if (h->score_recorded) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->ev_score_done, 0));     // workspace shared with arx_score callers
   if (slot_used) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_done[s], 0));
   int rc = score_impl(h, 0, din, nullptr, n_windows, dlog, disc ? dist : nullptr, dch, nullptr, nullptr, h->hs_comp);
   if (rc) return rc;

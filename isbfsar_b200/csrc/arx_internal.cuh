@@ -41,6 +41,9 @@ struct ArxTransformer {
   ArxTcLinear tl_uab;        // 32 composite columns Wdr.Wv of the second-generation head pass
   float *wc = nullptr, *tcomp = nullptr;   // composite weights (32,F) and table (T,32)
   __half *uc_img = nullptr;  // per class Wdr.Vc^T (16 x 128 fp16 B operand)
+  // tiled operands of the any-N kernel (arx_tcn.cu): [way][Npad/128] 32 KB tiles
+  __half *kc_tiles = nullptr, *vct_tiles = nullptr, *uc_tiles = nullptr;
+  uint32_t *tup_packed = nullptr;   // (N) tuple frames packed one byte each
 };
 
 // Replayable CUDA graphs of the arx_score kernel chain for one (buffers, batch, support geometry, weights) key: the
@@ -93,6 +96,7 @@ struct arx_handle {
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_aux_fork = nullptr, ev_aux_done = nullptr;
   bool support_recorded = false, score_recorded = false;
+  unsigned long long support_cid = 0, score_cid = 0;   // capture the events were last recorded in (0 = eagerly), see arx_api.cu
   cudaStream_t last_score_stream = nullptr;   // stream of the last scoring pass (ev_score_done was recorded there)
   float *ss_poses = nullptr;       // copy of the support poses when the features were produced on tensor cores
   bool ss_poses_valid = false;
@@ -130,7 +134,11 @@ struct arx_handle {
   // one-time per-DEVICE initialisation done by this handle (__constant__ tables, function attributes): kept per handle,
   // not process-wide, so a second handle on another GPU of the same process initialises its own device
   uint32_t dev_init = 0;
+  uint32_t warned = 0;              // per-transformer: the fp32-fallback notice was printed
   std::unordered_map<const void *, int> smem_attr;   // dynamic shared-memory limit already set per kernel (saves a driver call per launch)
+  float *zscratch = nullptr;        // softmax normaliser partials of the tiled attention kernel (arx_tcn.cu), per CTA
+  size_t zscratch_bytes = 0;
+  int *tcn_diag = nullptr;          // watchdog record of the tiled attention kernel
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
   int attn_poly = 0;         // k_attn_tc3: every attn_poly-th register pair takes the FMA-pipe exp2 polynomial (0 = none; debug key 4)
@@ -268,6 +276,16 @@ int arx_tcp_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img,
 int arx_tcp_linear_chunked(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *gc, cudaStream_t st);
 int arx_tuple_img(arx_handle *h, const ArxTransformer &tr, const float *gc, int n_chunks, int64_t n_win, __half *kq_img, float alpha,
                   cudaStream_t st);
+
+// ---- tiled any-N tcgen05 attention (arx_tcn.cu)
+bool arx_tcn_supported(const arx_handle *h, const ArxTransformer &tr);
+bool arx_tcn_needs_rowmax(const ArxTransformer &tr);
+int arx_tcn_prep_support(arx_handle *h, ArxTransformer &tr, int way, bool with_head, cudaStream_t st);
+int arx_tcn_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int ldg, int64_t n_win, __half *kq_tiles, cudaStream_t st);
+int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
+                      float *partial, float *logits, int32_t *chosen, cudaStream_t st);
+int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
+                 float *uab, float *y, __half *y_img, int y_nk, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

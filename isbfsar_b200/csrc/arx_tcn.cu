@@ -1,0 +1,742 @@
+// tcgen05 cross-attention + distances for ANY tuple count N, tiled over blocks of 128 tuples
+// (T=32 pairs N=496 -> 4 tiles, T=16 triples N=560 -> 5, T=32 triples N=4960 -> 39; also N <= 128 for other T).
+//
+// Reference semantics (modules/ar/utils/model.py:95-135), per (query window b, class c):
+//   S = Kq.Kc^T / sqrt(D);  P = softmax(S, dim=-2)  -- normalised over the QUERY tuples, per support tuple s;
+//   proto = P.Vc;  logit = -||Vq - proto||_F^2 / N.
+// The softmax axis (q) is not the contraction axis of the prototype (s), so flash-attention's online rescaling does
+// not apply: the normaliser Z[s] = sum_q exp(S[q,s]) needs ALL query tiles before any P can be formed.
+// Two passes per (window, class), both on the schedule of the third-generation kernel (arx_tc3.cu):
+//   pass A  for every pair of query tiles (qt0|qt1) and every support tile st:
+//             MMA1  S^T[s, (q of qt0 | q of qt1)] = Kc[st] . Kq'^T   (M=128, N=256, K=128, fp16 operands)
+//             the two softmax warpgroups take one 128-column half each: exp2, thread-local row sum (thread == TMEM
+//             lane == support tuple s) accumulated into Z[st*128+s]
+//   pass B  same tiles again: exp2 recomputed, P = E / Z[s] written to shared memory as the MN-major bf16 B operand,
+//             MMA2  proto^T[d, q] += Vc^T[st][d, :] . P[q, :]   accumulated over st in TMEM (one accumulator per query
+//             tile of the pair); after the last st the epilogue warps form  sum_q (Vq[q][d] - proto[q][d])^2  with
+//             Vq[q][d] = sum_p Gv_p[frame_p(q)][d] rebuilt from the per-frame V projections (tuple features never exist).
+// N <= 128 (one query tile) needs no pass A: the row sum of the only tile is the normaliser.
+// The exponentials are computed twice (1.67x the exps of a single pass would need E kept on chip: N=496 alone is
+// 512 KB of bf16 per class); MUFU.EX2 stays the co-limiting pipe exactly as in the N=120 kernel.
+// MODE 1 (open-set head, model.py:323-324,196): same pipeline for the winning class only, with Uc = Wdr.Vc^T (rows l)
+// in place of Vc^T, so the accumulator is sum_s P[q,s].(Wdr.Vc[s])[l] and the epilogue writes
+//   y[q][l] = (Wdr.Vq[q] + bdr)[l] - acc[l][q]    (head by linearity)
+// straight into the fp16 activation image of discriminator.fc1.
+// ROWMAX variant: subtracts a running row maximum before exp2 (online rescaling of Z across query tiles), for
+// LayerNorm affines outside the static bound under which exp2 needs no shift.
+// Work unit = (window, class), round-robin over one persistent CTA per SM; 16 warps, warp-specialised; every
+// mbarrier wait carries a watchdog (a protocol bug traps instead of hanging the GPU).
+#include "arx_internal.cuh"
+#include "arx_ptx.cuh"
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+namespace {
+using namespace ptx;
+
+constexpr int DD = 128;
+constexpr uint32_t IMG_BYTES = 128 * DD * 2;
+constexpr uint32_t SUB_BYTES = 128 * 64 * 2;
+constexpr int NTHREADS = 512;
+
+constexpr uint32_t OFF_KQ = 0;                       // 64 KB: [sub0: t0 rows | t1 rows][sub1: t0 rows | t1 rows]
+constexpr uint32_t OFF_KC = 2 * IMG_BYTES;           // 32 KB
+constexpr uint32_t OFF_VCT = 3 * IMG_BYTES;          // 2 x 32 KB
+constexpr uint32_t OFF_P = 5 * IMG_BYTES;            // 2 x 32 KB (one per softmax group / query tile of the pair)
+constexpr uint32_t OFF_BAR = 7 * IMG_BYTES;
+enum { B_FULL_KQ = 0, B_EMPTY_KQ = 1, B_FULL_KC = 2, B_EMPTY_KC = 3, B_FULL_VC = 4, B_EMPTY_VC = 6, B_S_FULL = 8, B_S_EMPTY = 9,
+       B_P_FULL = 10, B_P_EMPTY = 12, B_O_FULL = 14, B_O_EMPTY = 16, B_XU = 18, B_COUNT = 20 };
+constexpr uint32_t SMEM_BYTES = OFF_BAR + B_COUNT * 8 + 16 + 1024;
+
+struct AttnNParams {
+  const __half *kq_img;     // [n_win][nq] 32 KB tiles, K-major SW128, rows = query tuples (LayerNorm-ed, pre-scaled by log2e/sqrt(D))
+  const __half *kc_img;     // [classes][ns] tiles, rows = support tuples
+  const __half *vct_img;    // [classes][ns] tiles, rows = d (mode 0: Vc^T) or l (mode 1: Uc), cols = support tuples, bf16
+  const float *tab;         // per-frame table, row (win*T + t): part p of lane x at tab[row*tab_ld + tab_off + p*tab_pstride + x]
+  const uint32_t *tup;      // [N] tuple frames packed i | j << 8 | k << 16
+  const int32_t *chosen;    // mode 1: class of every window
+  float *partial;           // mode 0: [n_win*way][4] squared-distance partials (one per epilogue warp)
+  float *y;                 // mode 1: fp32 [n_win][N*L], or
+  __half *y_img;            //         fp16 activation image [ceil(n_win/128)][y_nk][128 x 64]
+  float *zscratch;          // [grid][2 unit parity][2 groups][2: Z | M][ns*128]
+  int *diag;                // watchdog record (see mbar_wait_wd)
+  int n_win, way, N, T, c, nq, ns, tab_ld, tab_off, tab_pstride, mode, L, y_nk;
+};
+
+// Watchdog wait: a protocol bug must not hang the GPU.  On a timeout (~1 s) the first thread to notice records
+// (barrier index, parity, role, step) in p.diag and every waiter of the CTA grid bails out; the launcher reports it.
+__device__ __forceinline__ void mbar_wait_wd_(uint64_t *bar, uint32_t parity, int *diag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0u) {
+      if (*reinterpret_cast<volatile int *>(diag) != 0) return;
+      if (clock64() - t0 > 2000000000LL) {
+        if (atomicCAS(diag, 0, code | 0x40000000) == 0) { diag[1] = (int)blockIdx.x; diag[2] = (int)threadIdx.x; diag[3] = (int)parity; }
+        return;
+      }
+    }
+  }
+}
+#define mbar_wait_wd(bar, parity) mbar_wait_wd_((bar), (parity), p.diag, (int)((bar) - bars) | (__LINE__ << 8))
+
+__device__ __forceinline__ uint32_t ex2_bits(uint32_t x) {
+  uint32_t y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool ROWMAX>
+__global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + B_COUNT * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool head = p.mode == 1;
+  const int n_units = head ? p.n_win : p.n_win * p.way;
+  const int my_units = n_units > (int)blockIdx.x ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int nq = p.nq, ns = p.ns, nqp = (nq + 1) >> 1;
+  const int pass0 = nq == 1 ? 1 : 0;                   // a single query tile needs no normaliser pass
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[B_FULL_KQ], 1); mbar_init(&bars[B_EMPTY_KQ], 1);
+    mbar_init(&bars[B_FULL_KC], 1); mbar_init(&bars[B_EMPTY_KC], 1);
+    mbar_init(&bars[B_S_FULL], 1); mbar_init(&bars[B_S_EMPTY], 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[B_FULL_VC + i], 1); mbar_init(&bars[B_EMPTY_VC + i], 1);
+      mbar_init(&bars[B_P_FULL + i], 128); mbar_init(&bars[B_P_EMPTY + i], 1);
+      mbar_init(&bars[B_O_FULL + i], 1); mbar_init(&bars[B_O_EMPTY + i], 128);
+      mbar_init(&bars[B_XU + i], 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 3) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t TM_S = tmem, TM_O = tmem + 256;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0) {
+      if (elect_one()) {            // producer: class operands -- Kc every step (single-buffered), Vc^T/Uc in pass B (2-stage ring)
+        int k = 0, kb = 0;
+        for (int ui = 0; ui < my_units; ++ui) {
+          const int u = blockIdx.x + ui * gridDim.x;
+          const size_t cls = head ? (size_t)p.chosen[u] : (size_t)(u % p.way);
+          const uint8_t *kc0 = reinterpret_cast<const uint8_t *>(p.kc_img) + cls * ns * IMG_BYTES;
+          const uint8_t *vc0 = reinterpret_cast<const uint8_t *>(p.vct_img) + cls * ns * IMG_BYTES;
+          for (int pass = pass0; pass < 2; ++pass)
+            for (int qp = 0; qp < nqp; ++qp)
+              for (int st = 0; st < ns; ++st, ++k) {
+                const uint8_t *kc = kc0 + (size_t)st * IMG_BYTES;
+                mbar_wait_wd(&bars[B_EMPTY_KC], (k & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars[B_FULL_KC], IMG_BYTES);
+                bulk_g2s(smem + OFF_KC, kc, SUB_BYTES, &bars[B_FULL_KC]);
+                bulk_g2s(smem + OFF_KC + SUB_BYTES, kc + SUB_BYTES, SUB_BYTES, &bars[B_FULL_KC]);
+                if (pass == 1) {
+                  const uint8_t *vc = vc0 + (size_t)st * IMG_BYTES;
+                  const int sg = kb & 1;
+                  mbar_wait_wd(&bars[B_EMPTY_VC + sg], ((kb >> 1) & 1) ^ 1);
+                  mbar_arrive_expect_tx(&bars[B_FULL_VC + sg], IMG_BYTES);
+                  bulk_g2s(smem + OFF_VCT + sg * IMG_BYTES, vc, SUB_BYTES, &bars[B_FULL_VC + sg]);
+                  bulk_g2s(smem + OFF_VCT + sg * IMG_BYTES + SUB_BYTES, vc + SUB_BYTES, SUB_BYTES, &bars[B_FULL_VC + sg]);
+                  ++kb;
+                }
+              }
+        }
+      }
+    } else if (warp == 2) {
+      if (elect_one()) {            // producer: the pair of query tiles, interleaved into one 256-row K-major B operand
+        int kq = 0;
+        for (int ui = 0; ui < my_units; ++ui) {
+          const int u = blockIdx.x + ui * gridDim.x;
+          const size_t win = head ? (size_t)u : (size_t)(u / p.way);
+          const uint8_t *q0 = reinterpret_cast<const uint8_t *>(p.kq_img) + win * nq * IMG_BYTES;
+          for (int pass = pass0; pass < 2; ++pass)
+            for (int qp = 0; qp < nqp; ++qp, ++kq) {
+              const int nw = min(2, nq - 2 * qp);
+              mbar_wait_wd(&bars[B_EMPTY_KQ], (kq & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars[B_FULL_KQ], nw * IMG_BYTES);
+              for (int w = 0; w < nw; ++w) {
+                const uint8_t *src = q0 + (size_t)(2 * qp + w) * IMG_BYTES;
+                bulk_g2s(smem + OFF_KQ + w * SUB_BYTES, src, SUB_BYTES, &bars[B_FULL_KQ]);                              // d 0..63
+                bulk_g2s(smem + OFF_KQ + 2 * SUB_BYTES + w * SUB_BYTES, src + SUB_BYTES, SUB_BYTES, &bars[B_FULL_KQ]);  // d 64..127
+              }
+              // the next pair is needed ns steps from now and its load is exposed (single buffer): have it wait in L2
+              const int nqp_next = qp + 1 < nqp ? qp + 1 : 0;
+              bulk_prefetch_l2(q0 + (size_t)(2 * nqp_next) * IMG_BYTES, min(2, nq - 2 * nqp_next) * IMG_BYTES);
+            }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {            // MMA1 issuer: one N=256 (N=128 for an unpaired last tile) MMA sequence per step
+        constexpr uint64_t DESC_K = smem_desc_sw128(16, 1024);
+        const uint32_t sbase = smem_u32(smem);
+        int k = 0, kq = 0;
+        for (int ui = 0; ui < my_units; ++ui)
+          for (int pass = pass0; pass < 2; ++pass)
+            for (int qp = 0; qp < nqp; ++qp, ++kq) {
+              const int nw = min(2, nq - 2 * qp);
+              const uint32_t idesc = nw == 2 ? idesc_f16(128, 256, 0, 0) : idesc_f16(128, 128, 0, 0);
+              mbar_wait_wd(&bars[B_FULL_KQ], kq & 1);
+              for (int st = 0; st < ns; ++st, ++k) {
+                mbar_wait_wd(&bars[B_FULL_KC], k & 1);
+                mbar_wait_wd(&bars[B_S_EMPTY], (k & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                  const uint32_t aoff = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
+                  const uint32_t boff = (kk >> 2) * (2 * SUB_BYTES) + (kk & 3) * 32;
+                  mma_f16_ss(TM_S, smem_desc_at(DESC_K, sbase + OFF_KC + aoff), smem_desc_at(DESC_K, sbase + OFF_KQ + boff), idesc, kk > 0);
+                }
+                mma_commit(&bars[B_S_FULL]);
+                mma_commit(&bars[B_EMPTY_KC]);
+                if (st == ns - 1) mma_commit(&bars[B_EMPTY_KQ]);
+              }
+            }
+      }
+    } else {
+      if (elect_one()) {            // MMA2 issuer (pass B): proto^T[d, q of tile w] += Vc^T[st] . P_w, accumulated over st
+        constexpr uint64_t DESC_K = smem_desc_sw128(16, 1024);
+        constexpr uint64_t DESC_MN = smem_desc_sw128(16384, 1024);
+        constexpr uint32_t IDESC2 = idesc_bf16(128, 128, 0, 1);
+        const uint32_t sbase = smem_u32(smem);
+        int kb = 0, ke = 0;
+        for (int ui = 0; ui < my_units; ++ui)
+          for (int qp = 0; qp < nqp; ++qp, ++ke) {
+            const int nw = min(2, nq - 2 * qp);
+            for (int st = 0; st < ns; ++st, ++kb) {
+              const int sg = kb & 1;
+              mbar_wait_wd(&bars[B_FULL_VC + sg], (kb >> 1) & 1);
+              for (int w = 0; w < nw; ++w) {
+                mbar_wait_wd(&bars[B_P_FULL + w], kb & 1);
+                if (st == 0) mbar_wait_wd(&bars[B_O_EMPTY + w], (ke & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                  const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
+                  mma_f16_ss(TM_O + w * 128, smem_desc_at(DESC_K, sbase + OFF_VCT + sg * IMG_BYTES + off),
+                             smem_desc_at(DESC_MN, sbase + OFF_P + w * IMG_BYTES + kk * 2048), IDESC2, (st > 0 || kk > 0) ? 1u : 0u);
+                }
+                if (st == ns - 1) mma_commit(&bars[B_O_FULL + w]);
+                mma_commit(&bars[B_P_EMPTY + w]);
+              }
+              if (nw == 1) {        // unpaired tile: slot 1's barriers complete the same phases, sequenced like a real tile (an
+                                    // mbarrier parity wait cannot tell phase k from k+2: nothing may run two phases ahead of its waiter)
+                mbar_wait_wd(&bars[B_P_FULL + 1], kb & 1);
+                if (st == 0) mbar_wait_wd(&bars[B_O_EMPTY + 1], (ke & 1) ^ 1);
+                if (st == ns - 1) mbar_arrive(&bars[B_O_FULL + 1]);
+                mbar_arrive(&bars[B_P_EMPTY + 1]);
+              }
+              mma_commit(&bars[B_EMPTY_VC + sg]);
+            }
+          }
+      }
+    }
+  } else if (warp < 12) {
+    // ---------------- softmax group g owns query tile g of every pair: S^T columns [128g, 128g+128), P buffer g
+    setmaxnreg_inc<160>();
+    const int g = (warp - 4) >> 2, quad = warp & 3;
+    const int s = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t *prow = smem + OFF_P + g * IMG_BYTES + (s >> 3) * 1024 + (s & 7) * 128;
+    const int NSP = ns * 128;
+    int k = 0, kb = 0;
+    for (int ui = 0; ui < my_units; ++ui) {
+      float *zme = p.zscratch + ((((size_t)blockIdx.x * 2 + (ui & 1)) * 2 + g) * 2) * NSP;      // this group's [Z | M]
+      const float *zot = p.zscratch + ((((size_t)blockIdx.x * 2 + (ui & 1)) * 2 + (g ^ 1)) * 2) * NSP;
+      for (int pass = pass0; pass < 2; ++pass) {
+        if (pass == 1 && pass0 == 0) {         // both groups' normaliser partials must be visible before pass B reads them
+          __threadfence_block();
+          named_bar_sync(1, 256);
+        }
+        for (int qp = 0; qp < nqp; ++qp) {
+          const int nw = min(2, nq - 2 * qp);
+          const int nvalid = p.N - (2 * qp + g) * 128;       // valid query columns of this group's tile (>= 128: all)
+          for (int st = 0; st < ns; ++st, ++k) {
+            const int zi = st * 128 + s;
+            float zinv = 0.f, mrow = 0.f;
+            if (pass == 1 && pass0 == 0 && g < nw) {          // normaliser of this support tuple over ALL query tiles (pass A)
+              if constexpr (ROWMAX) {
+                const float m0 = zme[NSP + zi], m1 = zot[NSP + zi];
+                mrow = fmaxf(m0, m1);
+                zinv = __frcp_rn(zme[zi] * ex2f(m0 - mrow) + zot[zi] * ex2f(m1 - mrow)) * 1.0028177f;
+              } else {
+                zinv = __frcp_rn(zme[zi] + zot[zi]) * 1.0028177f;       // centred truncation to bf16, see arx_tc2.cu
+              }
+            }
+            mbar_wait_wd(&bars[B_S_FULL], k & 1);
+            tc_fence_after();
+            if (g >= nw) {              // unpaired tile: this group has no columns, but its barriers keep their phase, in turn
+              mbar_arrive(&bars[B_S_EMPTY]);
+              mbar_wait_wd(&bars[B_XU + 0], k & 1);
+              mbar_arrive(&bars[B_XU + 1]);
+              if (pass == 1) {          // sequenced like a real P tile: without the wait this barrier could complete two
+                                        // phases while the MMA2 issuer is held up behind a slow epilogue (seen on the GPU)
+                mbar_wait_wd(&bars[B_P_EMPTY + 1], (kb & 1) ^ 1);
+                mbar_arrive(&bars[B_P_FULL + 1]);
+                ++kb;
+              }
+              continue;
+            }
+            uint32_t r[128];
+            tmem_ld32(TM_S + lane_base + g * 128 + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            tmem_ld32(TM_S + lane_base + g * 128 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            tmem_ld32(TM_S + lane_base + g * 128 + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+            tmem_ld32(TM_S + lane_base + g * 128 + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[B_S_EMPTY]);
+            // MUFU token: the groups take turns on the exp phase so that one's loads / sums / stores run under the other's MUFU stream
+            if (g == 0) { if (k > 0) mbar_wait_wd(&bars[B_XU + 1], (k - 1) & 1); }
+            else mbar_wait_wd(&bars[B_XU + 0], k & 1);
+            float zscale = 0.f;             // ROWMAX pass A: factor that brings the running sum to the new maximum
+            if constexpr (ROWMAX) {
+              if (pass == 0 || pass0 == 1) {
+                float mt = -INFINITY;
+                if (nvalid >= 128) {
+#pragma unroll
+                  for (int j = 0; j < 128; ++j) mt = fmaxf(mt, __uint_as_float(r[j]));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 128; ++j) mt = fmaxf(mt, j < nvalid ? __uint_as_float(r[j]) : -INFINITY);
+                }
+                if (pass0 == 0 && qp > 0) {
+                  const float mo = zme[NSP + zi];
+                  mrow = fmaxf(mo, mt);
+                  zscale = ex2f(mo - mrow);
+                } else {
+                  mrow = mt;
+                }
+              }
+              const uint64_t mm = pack2(-mrow, -mrow);
+#pragma unroll
+              for (int j = 0; j < 128; j += 2) {
+                const uint64_t v = add2(pack2u(r[j], r[j + 1]), mm);
+                r[j] = (uint32_t)v; r[j + 1] = (uint32_t)(v >> 32);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 128; ++j) r[j] = ex2_bits(r[j]);
+            mbar_arrive(&bars[B_XU + g]);
+            if (pass == 0 || pass0 == 1) {
+              // row sum over the valid query columns (pad columns of the last tile have S = 0, exp = 1: masked out)
+              if (nvalid < 128) {
+#pragma unroll
+                for (int j = 0; j < 128; ++j) r[j] = j < nvalid ? r[j] : 0u;
+              }
+              uint64_t z0 = 0ull, z1 = 0ull, z2 = 0ull, z3 = 0ull;
+#pragma unroll
+              for (int q = 0; q < 64; q += 4) {
+                z0 = add2v(z0, pack2u(r[2 * q], r[2 * q + 1]));
+                z1 = add2v(z1, pack2u(r[2 * q + 2], r[2 * q + 3]));
+                z2 = add2v(z2, pack2u(r[2 * q + 4], r[2 * q + 5]));
+                z3 = add2v(z3, pack2u(r[2 * q + 6], r[2 * q + 7]));
+              }
+              float zl, zh;
+              unpack2(add2(add2(z0, z1), add2(z2, z3)), zl, zh);
+              const float zs = zl + zh;
+              if (pass == 0) {
+                if constexpr (ROWMAX) {
+                  zme[zi] = qp > 0 ? zme[zi] * zscale + zs : zs;
+                  zme[NSP + zi] = mrow;
+                } else {
+                  zme[zi] = qp > 0 ? zme[zi] + zs : zs;
+                }
+                continue;
+              }
+              zinv = __frcp_rn(zs) * 1.0028177f;          // single query tile: the tile's own row sum is the normaliser
+            }
+            const uint64_t zz = pack2(zinv, zinv);
+            mbar_wait_wd(&bars[B_P_EMPTY + g], (kb & 1) ^ 1);
+#pragma unroll
+            for (int c16 = 0; c16 < 16; ++c16) {
+              uint32_t hh[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint64_t m = mul2(pack2u(r[c16 * 8 + 2 * q], r[c16 * 8 + 2 * q + 1]), zz);
+                hh[q] = __byte_perm((uint32_t)m, (uint32_t)(m >> 32), 0x7632);
+              }
+              *reinterpret_cast<uint4 *>(prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (s & 7)) << 4)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[B_P_FULL + g]);
+            ++kb;
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: thread == TMEM lane == output dimension d (mode 0) or head column l (mode 1)
+    // Vq[q][lane] = sum_p tab_p[frame_p(q)][lane] is gathered from the per-frame table (L1/L2 resident, 128-byte coalesced
+    // rows) one 32-column chunk AHEAD of the accumulator chunk it is compared with: the tuple words of a chunk are one
+    // coalesced load, broadcast by shuffles, and all table loads of a chunk are issued back to back (no dependent chains --
+    // a first version that loaded per column ran at ~150 K clk per tile and throttled the whole kernel).
+    setmaxnreg_inc<152>();
+    const int quad = warp & 3;
+    const int d = quad * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    const bool c3 = p.c == 3;
+    const size_t ld = (size_t)p.tab_ld;
+    const int ps = p.tab_pstride;
+    int ke = 0;
+    for (int ui = 0; ui < my_units; ++ui) {
+      const int u = blockIdx.x + ui * gridDim.x;
+      const int win = head ? u : u / p.way;
+      const float *tb = p.tab + (size_t)win * p.T * p.tab_ld + p.tab_off + d;
+      auto gather = [&](int qc, float (&v)[32]) {        // Vq of columns qc .. qc+31 (clamped: pad columns are masked later)
+        const uint32_t tpl = __ldg(p.tup + min(qc + lane, p.N - 1));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t tp = __shfl_sync(0xffffffffu, tpl, j);
+          float x = __ldg(tb + (size_t)(tp & 0xffu) * ld) + __ldg(tb + (size_t)((tp >> 8) & 0xffu) * ld + ps);
+          if (c3) x += __ldg(tb + (size_t)((tp >> 16) & 0xffu) * ld + 2 * ps);
+          v[j] = x;
+        }
+      };
+      float run = 0.f;
+      for (int qp = 0; qp < nqp; ++qp, ++ke) {
+        const int nw = min(2, nq - 2 * qp);
+        for (int w = 0; w < 2; ++w) {
+          if (w >= nw) {
+            mbar_wait_wd(&bars[B_O_FULL + w], ke & 1);
+            mbar_arrive(&bars[B_O_EMPTY + w]);
+            continue;
+          }
+          const int q0 = (2 * qp + w) * 128;
+          float va[32], vb[32];
+          gather(q0, va);                                  // in flight while the last MMA2 of the tile completes
+          mbar_wait_wd(&bars[B_O_FULL + w], ke & 1);
+          tc_fence_after();
+          auto chunk = [&](int ch, const float (&v)[32], float (&vn)[32]) {
+            uint32_t r[32];
+            tmem_ld32(TM_O + lane_base + w * 128 + ch * 32, r);
+            if (ch < 3) gather(q0 + (ch + 1) * 32, vn);
+            tmem_ld_wait();
+            if (ch == 3) { tc_fence_before(); mbar_arrive(&bars[B_O_EMPTY + w]); }
+            const int qc = q0 + ch * 32;
+            if (!head) {
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+              for (int jj = 0; jj < 32; jj += 2) {
+                const float d0 = qc + jj < p.N ? v[jj] - __uint_as_float(r[jj]) : 0.f;
+                const float d1 = qc + jj + 1 < p.N ? v[jj + 1] - __uint_as_float(r[jj + 1]) : 0.f;
+                a0 = fmaf(d0, d0, a0);
+                a1 = fmaf(d1, d1, a1);
+              }
+              run += a0 + a1;
+            } else if (d < p.L) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) {
+                const int q = qc + jj;
+                if (q < p.N) {
+                  const float df = v[jj] - __uint_as_float(r[jj]);
+                  const int col = q * p.L + d;
+                  if (p.y_img) {
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(p.y_img) + ((size_t)(win >> 7) * p.y_nk + (col >> 6)) * (128 * 128);
+                    *reinterpret_cast<__half *>(dst + sw128_offset(win & 127, col & 63)) = __float2half_rn(df);
+                  } else {
+                    p.y[(size_t)win * p.N * p.L + col] = df;
+                  }
+                }
+              }
+            }
+          };
+          chunk(0, va, vb);
+          chunk(1, vb, va);
+          chunk(2, va, vb);
+          chunk(3, vb, va);
+        }
+      }
+      if (!head) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) run += __shfl_xor_sync(0xffffffffu, run, o);
+        if (lane == 0) p.partial[(size_t)u * 4 + quad] = run;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ---- operand image builders (tiled) ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf162(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// Query K tiles: one warp per tuple row; K = LayerNorm(sum_p Gk_p[frame_p]) * alpha -> fp16, K-major SW128.  grid (n_win, nq)
+__global__ void __launch_bounds__(256) k_prep_kq_tiles(const float *__restrict__ G, const uint32_t *__restrict__ tup, const float *__restrict__ ln_g,
+                                                       const float *__restrict__ ln_b, __half *__restrict__ img, int T, int c, int N, int nq, int ldg,
+                                                       float alpha) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t seq = blockIdx.x;
+  const int qt = blockIdx.y;
+  uint8_t *out = reinterpret_cast<uint8_t *>(img) + (seq * nq + qt) * IMG_BYTES;
+  const int d0 = lane * 4;
+  const float4 g = *reinterpret_cast<const float4 *>(ln_g + d0);
+  const float4 be = *reinterpret_cast<const float4 *>(ln_b + d0);
+  for (int r = warp; r < 128; r += 8) {
+    const int q = qt * 128 + r;
+    uint2 packed = make_uint2(0u, 0u);
+    if (q < N) {
+      const uint32_t tp = tup[q];
+      float4 k = make_float4(0, 0, 0, 0);
+      for (int pp = 0; pp < c; ++pp) {
+        const int fr = (tp >> (8 * pp)) & 0xff;
+        const float4 a = *reinterpret_cast<const float4 *>(G + (seq * T + fr) * (size_t)ldg + pp * DD + d0);
+        k.x += a.x; k.y += a.y; k.z += a.z; k.w += a.w;
+      }
+      float sm = k.x + k.y + k.z + k.w;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      const float mean = sm / DD;
+      const float4 dl = make_float4(k.x - mean, k.y - mean, k.z - mean, k.w - mean);
+      float qq = dl.x * dl.x + dl.y * dl.y + dl.z * dl.z + dl.w * dl.w;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+      const float rstd = 1.0f / sqrtf(qq / DD + 1e-5f);
+      packed.x = pack_half2((dl.x * rstd * g.x + be.x) * alpha, (dl.y * rstd * g.y + be.y) * alpha);
+      packed.y = pack_half2((dl.z * rstd * g.z + be.z) * alpha, (dl.w * rstd * g.w + be.w) * alpha);
+    }
+    *reinterpret_cast<uint2 *>(out + (d0 >> 6) * SUB_BYTES + sw128_offset(r, d0 & 63)) = packed;
+  }
+}
+
+// Support K tiles from fp32 ks (way, N, D): rows = s, cols = d.  grid (way, ns)
+__global__ void __launch_bounds__(256) k_prep_kc_tiles(const float *__restrict__ ks, __half *__restrict__ img, int N, int ns) {
+  const size_t cls = blockIdx.x;
+  const int st = blockIdx.y;
+  const float *k = ks + cls * (size_t)N * DD;
+  uint8_t *out = reinterpret_cast<uint8_t *>(img) + (cls * ns + st) * IMG_BYTES;
+  for (int e = threadIdx.x; e < 128 * 16; e += 256) {
+    const int dc = e & 15, r = e >> 4, s = st * 128 + r;
+    uint4 pk = make_uint4(0, 0, 0, 0);
+    if (s < N) {
+      const float4 x0 = *reinterpret_cast<const float4 *>(k + (size_t)s * DD + dc * 8);
+      const float4 x1 = *reinterpret_cast<const float4 *>(k + (size_t)s * DD + dc * 8 + 4);
+      pk.x = pack_half2(x0.x, x0.y); pk.y = pack_half2(x0.z, x0.w); pk.z = pack_half2(x1.x, x1.y); pk.w = pack_half2(x1.z, x1.w);
+    }
+    const int d0 = dc * 8;
+    *reinterpret_cast<uint4 *>(out + (d0 >> 6) * SUB_BYTES + sw128_offset(r, d0 & 63)) = pk;
+  }
+}
+
+// Support V^T tiles (bf16): rows = d, cols = support tuple of tile st (zero beyond N).  grid (way, ns)
+__global__ void __launch_bounds__(256) k_prep_vct_tiles(const float *__restrict__ vs, __half *__restrict__ img, int N, int ns) {
+  const size_t cls = blockIdx.x;
+  const int st = blockIdx.y;
+  const float *v = vs + cls * (size_t)N * DD;
+  uint8_t *out = reinterpret_cast<uint8_t *>(img) + (cls * ns + st) * IMG_BYTES;
+  for (int e = threadIdx.x; e < DD * 16; e += 256) {
+    const int d = e & 127, sc = e >> 7;          // consecutive threads -> consecutive d (coalesced reads)
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int s = st * 128 + sc * 8 + i;
+      x[i] = s < N ? v[(size_t)s * DD + d] : 0.f;
+    }
+    uint4 pk;
+    pk.x = pack_bf162(x[0], x[1]); pk.y = pack_bf162(x[2], x[3]); pk.z = pack_bf162(x[4], x[5]); pk.w = pack_bf162(x[6], x[7]);
+    const int s0 = sc * 8;
+    *reinterpret_cast<uint4 *>(out + (s0 >> 6) * SUB_BYTES + sw128_offset(d, s0 & 63)) = pk;
+  }
+}
+
+// Head operand Uc tiles (bf16): rows l < L hold sum_d Wdr[l][d].Vc[s][d], rows >= L are zero.  grid (way, ns), 128 threads (one per s)
+__global__ void __launch_bounds__(128) k_prep_uc_tiles(const float *__restrict__ vs, const float *__restrict__ dr_w, __half *__restrict__ img, int N,
+                                                       int ns, int L) {
+  extern __shared__ float w_s[];                 // [L][128]
+  for (int e = threadIdx.x; e < L * 128; e += 128) w_s[e] = dr_w[e];
+  __syncthreads();
+  const size_t cls = blockIdx.x;
+  const int st = blockIdx.y, r = threadIdx.x, s = st * 128 + r;
+  uint8_t *out = reinterpret_cast<uint8_t *>(img) + (cls * ns + st) * IMG_BYTES;
+  float acc[32];
+#pragma unroll
+  for (int l = 0; l < 32; ++l) acc[l] = 0.f;
+  if (s < N) {
+    const float4 *v = reinterpret_cast<const float4 *>(vs + (cls * N + s) * DD);
+    for (int d4 = 0; d4 < 32; ++d4) {
+      const float4 x = v[d4];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        if (l < L) {
+          const float4 ww = *reinterpret_cast<const float4 *>(&w_s[l * 128 + d4 * 4]);
+          acc[l] += x.x * ww.x + x.y * ww.y + x.z * ww.z + x.w * ww.w;
+        }
+      }
+    }
+  }
+  // column r of the tile for every row: rows l < 32 carry values, rows 32..127 zero
+  for (int l = 0; l < 128; ++l) {
+    float val = 0.f;
+#pragma unroll
+    for (int m = 0; m < 32; ++m) if (m == l) val = acc[m];
+    *reinterpret_cast<__nv_bfloat16 *>(out + (r >> 6) * SUB_BYTES + sw128_offset(l, r & 63)) = __float2bfloat16_rn(l < L ? val : 0.f);
+  }
+}
+
+// Head table: UAB[row][p*32 + l] = sum_d Wdr[l][d] . Gv_p[row][d] (+ bdr[l] for p == 0); rows = n_win*T, pair tuples
+__global__ void __launch_bounds__(128) k_head_uab(const float *__restrict__ G, int ldg, int voff, const float *__restrict__ dr_w,
+                                                  const float *__restrict__ dr_b, float *__restrict__ uab, int64_t rows, int L) {
+  __shared__ float g_s[2 * DD];
+  const int64_t row = blockIdx.x;
+  if (row >= rows) return;
+  for (int e = threadIdx.x; e < 2 * DD; e += 128) g_s[e] = G[row * ldg + voff + e];
+  __syncthreads();
+  const int pp = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (pp < 2) {
+    float a = 0.f;
+    if (l < L) {
+      a = pp == 0 ? dr_b[l] : 0.f;
+      const float *w = dr_w + (size_t)l * DD;
+      for (int dd = 0; dd < DD; ++dd) a = fmaf(w[dd], g_s[pp * DD + dd], a);
+    }
+    uab[row * 64 + pp * 32 + l] = a;
+  }
+}
+
+__global__ void k_pack_tuples(const int32_t *__restrict__ tuples, uint32_t *__restrict__ out, int N, int c) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= N) return;
+  uint32_t v = 0;
+  for (int pp = 0; pp < c; ++pp) v |= (uint32_t)tuples[q * c + pp] << (8 * pp);
+  out[q] = v;
+}
+
+__global__ void k_finish_n(const float *__restrict__ partial, float *__restrict__ logits, int32_t *__restrict__ chosen, int64_t n_win, int way,
+                           int N) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_win) return;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int c = 0; c < way; ++c) {
+    const float4 t = *reinterpret_cast<const float4 *>(partial + (b * way + c) * 4);
+    const float lg = -(((t.x + t.y) + (t.z + t.w)) / (float)N);
+    logits[b * way + c] = lg;
+    if (lg > best) { best = lg; bi = c; }        // strict '>': the first maximum wins (torch.argmax, model.py:323)
+  }
+  if (chosen) chosen[b] = bi;
+}
+
+}  // namespace
+
+bool arx_tcn_supported(const arx_handle *h, const ArxTransformer &tr) {
+  return h->D == DD && h->T <= 255 && tr.c >= 2 && tr.c <= 3;
+}
+// exp2 without a shift is only safe inside the static LayerNorm bound; outside it the ROWMAX variant runs
+bool arx_tcn_needs_rowmax(const ArxTransformer &tr) { return !(tr.softmax_bound * ARX_SOFTMAX_LOG2E < 100.0f); }
+
+int arx_tcn_prep_support(arx_handle *h, ArxTransformer &tr, int way, bool with_head, cudaStream_t st) {
+  const int ns = tr.Npad / 128;
+  const size_t bytes = (size_t)h->way_cap * ns * IMG_BYTES;
+  if (!tr.kc_tiles) {
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.kc_tiles), bytes));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.vct_tiles), bytes));
+  }
+  if (!tr.tup_packed) {
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.tup_packed), (size_t)tr.N * sizeof(uint32_t)));
+    k_pack_tuples<<<(tr.N + 127) / 128, 128, 0, st>>>(tr.tuples, tr.tup_packed, tr.N, tr.c);
+    ARX_LAUNCH_CHECK(h);
+  }
+  k_prep_kc_tiles<<<dim3(way, ns), 256, 0, st>>>(tr.ks, tr.kc_tiles, tr.N, ns);
+  ARX_LAUNCH_CHECK(h);
+  k_prep_vct_tiles<<<dim3(way, ns), 256, 0, st>>>(tr.vs, tr.vct_tiles, tr.N, ns);
+  ARX_LAUNCH_CHECK(h);
+  if (with_head) {
+    if (!tr.uc_tiles) ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.uc_tiles), bytes));
+    k_prep_uc_tiles<<<dim3(way, ns), 128, h->T * 128 * sizeof(float), st>>>(tr.vs, h->dr_w, tr.uc_tiles, tr.N, ns, h->T);
+    ARX_LAUNCH_CHECK(h);
+  }
+  return ARX_OK;
+}
+
+int arx_tcn_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int ldg, int64_t n_win, __half *kq_tiles, cudaStream_t st) {
+  const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
+  const int nq = tr.Npad / 128;
+  for (int64_t b0 = 0; b0 < n_win; b0 += 32768) {
+    const int64_t nb = std::min<int64_t>(32768, n_win - b0);
+    k_prep_kq_tiles<<<dim3((unsigned)nb, nq), 256, 0, st>>>(G + b0 * h->T * ldg, tr.tup_packed, tr.ln_g, tr.ln_b,
+                                                           kq_tiles + (size_t)b0 * nq * 128 * DD, h->T, tr.c, tr.N, nq, ldg, alpha);
+    ARX_LAUNCH_CHECK(h);
+  }
+  return ARX_OK;
+}
+
+static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, int n_units, cudaStream_t st) {
+  const int grid = n_units < h->sm_count ? n_units : h->sm_count;
+  const size_t zbytes = (size_t)h->sm_count * 2 * 2 * 2 * tr.Npad * sizeof(float);
+  if (h->zscratch_bytes < zbytes) {
+    ARX_CUDA(h, cudaDeviceSynchronize());
+    cudaFree(h->zscratch);
+    h->zscratch = nullptr;
+    h->zscratch_bytes = 0;
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->zscratch), zbytes));
+    h->zscratch_bytes = zbytes;
+  }
+  p.zscratch = h->zscratch;
+  if (!h->tcn_diag) {
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->tcn_diag), 8 * sizeof(int)));
+    ARX_CUDA(h, cudaMemset(h->tcn_diag, 0, 8 * sizeof(int)));
+  }
+  p.diag = h->tcn_diag;
+  const bool rowmax = arx_tcn_needs_rowmax(tr);
+  auto kern = rowmax ? k_attn_tcn<true> : k_attn_tcn<false>;
+  { const int rc_ = arx_func_smem(h, kern, (int)SMEM_BYTES); if (rc_) return rc_; }
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
+  ARX_LAUNCH_CHECK(h);
+  if (getenv("ARX_TCN_CHECK")) {            // bring-up: synchronise and report a watchdog record
+    ARX_CUDA(h, cudaStreamSynchronize(st));
+    int d[4] = {0, 0, 0, 0};
+    ARX_CUDA(h, cudaMemcpy(d, h->tcn_diag, sizeof(d), cudaMemcpyDeviceToHost));
+    if (d[0]) {
+      cudaMemset(h->tcn_diag, 0, 8 * sizeof(int));
+      return arx_fail(h, ARX_ERR_CUDA, "tiled attention kernel: mbarrier wait timed out (barrier %d, source line %d, parity %d, block %d, thread %d, mode %d, nq %d)",
+                      d[0] & 0xff, (d[0] >> 8) & 0x3fffff, d[3], d[1], d[2], p.mode, p.nq);
+    }
+  }
+  return ARX_OK;
+}
+
+// logits (n_win, way) and chosen (n_win) of transformer `tr` from the query tiles; G = row-major per-frame projections
+int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
+                      float *partial, float *logits, int32_t *chosen, cudaStream_t st) {
+  AttnNParams p{};
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.vct_tiles; p.tab = G; p.tup = tr.tup_packed; p.partial = partial;
+  p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
+  p.tab_ld = ldg; p.tab_off = tr.c * h->D; p.tab_pstride = h->D; p.mode = 0;
+  int rc = tcn_launch(h, tr, p, (int)n_win * way, st);
+  if (rc) return rc;
+  k_finish_n<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
+}
+
+// open-set head input y = dimensionality_reduction(diff of the winning class) (model.py:323-324,196), pair tuples
+int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
+                 float *uab, float *y, __half *y_img, int y_nk, cudaStream_t st) {
+  if (tr.c != 2 || h->T > 32 || !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "tcn_head: pair tuples with T <= 32 only");
+  k_head_uab<<<(unsigned)(n_win * h->T), 128, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, n_win * h->T, h->T);
+  ARX_LAUNCH_CHECK(h);
+  AttnNParams p{};
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.uc_tiles; p.tab = uab; p.tup = tr.tup_packed; p.chosen = chosen;
+  p.y = y; p.y_img = y_img; p.y_nk = y_nk; p.L = h->T;
+  p.n_win = (int)n_win; p.way = 1; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
+  p.tab_ld = 64; p.tab_off = 0; p.tab_pstride = 32; p.mode = 1;
+  return tcn_launch(h, tr, p, (int)n_win, st);
+}

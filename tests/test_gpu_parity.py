@@ -334,31 +334,38 @@ def test_cfg5_heatmaps_to_scores_end_to_end(golden_dir):
     assert np.array_equal(logits[:80].argmax(1).cpu().numpy(), lo.argmax(1))
 
 
-def test_large_layernorm_affine_falls_back_to_fp32_kernels():
-    """exp2 without max-subtraction is only used inside the static LayerNorm bound; beyond it the
-    fp32 kernels with an online max take over -- results stay within tolerance."""
+def test_large_layernorm_affine_falls_back_to_fp32_kernels(capfd):
+    """exp2 without max-subtraction and fp16 QK^T operands are only used inside the static LayerNorm bound (DESIGN 4);
+    beyond it the fp32 kernels with an online max take over -- results stay within tolerance -- and the library says so
+    once on stderr.  force_path=2 keeps such weights on tensor cores (row-max variant of the tiled kernels): overflow
+    safe, but outside the 1e-3 tolerance, which is why it is not the default."""
     cfg = Cfg()
-    m, sd = make_model(cfg, 0)
-    with torch.no_grad():
-        m.transformers[0].norm_k.weight.fill_(3.0)
-    sd = dict(sd)
+    sd = dict(make_state_dict(cfg, 0))
     sd["transformers.0.norm_k.weight"] = np.full((128,), 3.0, np.float32)
     support, labels, query, _ = make_episode(cfg, 64, 71, "structured")
-    m.set_support(poses=torch.from_numpy(support[0]).cuda())
-    logits, is_true = m.score(torch.from_numpy(query).cuda())
-    assert m.last_path() == 1
     lo, it = TrxOracle(cfg, sd).score(support, labels, query)
-    assert rel_err(logits.cpu(), lo).max() < 1e-3 and rel_err(is_true.cpu(), it).max() < 1e-3
+    for force, path, tol in [(0, 1, 1e-3), (2, 3, 3e-2)]:
+        m, _ = make_model(cfg, 0, force_path=force)
+        with torch.no_grad():
+            m.transformers[0].norm_k.weight.fill_(3.0)
+        m.set_support(poses=torch.from_numpy(support[0]).cuda())
+        logits, is_true = m.score(torch.from_numpy(query).cuda())
+        logits2, _ = m.score(torch.from_numpy(query).cuda())
+        assert m.last_path() == path
+        assert rel_err(logits.cpu(), lo).max() < tol and rel_err(is_true.cpu(), it).max() < 1e-3
+        assert np.array_equal(logits.argmax(1).cpu().numpy(), lo.argmax(1))
+        err = capfd.readouterr().err
+        assert err.count("outside the fp16 tensor-core bound") == (1 if force == 0 else 0)      # said once, not per call
 
 
 def test_t8_runs_on_generic_tensor_core_kernels():
-    """T=8 pairs (N=28): first-generation tcgen05 kernel with the generic epilogue; fp32 open-set head."""
+    """T=8 pairs (N=28): tiled any-N tcgen05 kernels (single tile), head by linearity on the same kernel."""
     cfg = Cfg(seq_len=8)
     m, sd = make_model(cfg, 0)
     support, labels, query, _ = make_episode(cfg, 130, 81, "structured")
     m.set_support(poses=torch.from_numpy(support[0]).cuda())
     logits, is_true = m.score(torch.from_numpy(query).cuda())
-    assert m.last_path() == 2
+    assert m.last_path() == 3
     lo, it = TrxOracle(cfg, sd).score(support, labels, query)
     assert rel_err(logits.cpu(), lo).max() < TOL_TC and rel_err(is_true.cpu(), it).max() < TOL_TC
 
@@ -507,6 +514,7 @@ def test_cfg4_t32_pairs_64_windows_against_oracle():
     logits, is_true = m.score(torch.from_numpy(query).cuda())
     lo, it = TrxOracle(cfg, sd).score(support, labels, query, chunk=16)
     tol = tol_for(m)
+    assert m.last_path() == 3                       # tiled tcgen05 kernels: 4 query tiles x 4 support tiles, two passes
     assert rel_err(logits.cpu(), lo).max() < tol and rel_err(is_true.cpu(), it).max() < tol
     assert np.array_equal(logits.argmax(1).cpu().numpy(), lo.argmax(1)) and (lo.argmax(1) == planted).all()
     assert np.array_equal((is_true > 0.5).cpu().numpy(), it > 0.5)
@@ -525,6 +533,7 @@ def test_triples_against_oracle(T, way, B):
     with torch.no_grad():
         ssf = o.embed(torch.from_numpy(support))
         ref = o.cross_transformer(ssf.expand(B, -1, -1, -1), torch.from_numpy(labels).long(), o.embed(torch.from_numpy(query)).unsqueeze(1), ti=1)
+    assert m.last_path() == 3
     assert rel_err(logits, ref["logits"].numpy()).max() < tol_for(m)
     assert np.array_equal(logits.argmax(1), ref["logits"].numpy().argmax(1))
 
@@ -564,7 +573,7 @@ def test_add_hook_scores_match_oracle_probs():
     ref = TrxOracle(cfg, sd).forward({"sk": np.repeat(support, 3, 0)}, labels, {"sk": query}, want=("probs",))
     for c in range(5):
         got = scores[c].cpu().numpy()
-        np.testing.assert_allclose(got, ref["probs"][c].numpy(), rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(got, ref["probs"][c].numpy(), rtol=1e-3, atol=1e-7)     # the stated tolerance
         np.testing.assert_allclose(got.sum(axis=-2), 1.0, rtol=1e-5)
     true_index = 2                                       # the consumer's indexing (visualize_heatmaps.py:123)
     assert scores[true_index][0][0].shape == (120, 120)

@@ -35,16 +35,18 @@ def main():
         out.append({"config": "cfg3", "error": repr(e)})
     # cfg4 (i): 20-way, T=32, pairs N=496 (forward: logits + is_true)
     try:
-        cfg = Cfg(way=20, seq_len=32, temp_set=[2, 3]); m, sd = make_model(cfg, 0); B = 64
+        cfg = Cfg(way=20, seq_len=32, temp_set=[2, 3]); m, sd = make_model(cfg, 0); B = 2048
         support, labels, query, _ = make_episode(cfg, B, 71, "structured")
         m.set_support(poses=torch.from_numpy(support[0]).cuda()); Q = torch.from_numpy(query).cuda()
         ms = timed(lambda: m.score(Q), 3)
-        out.append({"config": "cfg4 20-way T=32 pairs N=496, B=64", "path": m.last_path(), "ms": ms, "windows_per_s": B / ms * 1e3})
+        out.append({"config": f"cfg4 20-way T=32 pairs N=496, B={B}", "path": m.last_path(), "ms": ms, "windows_per_s": B / ms * 1e3,
+                    "attention_tflops": 4 * 20 * 496 * 496 * 128 * B / ms / 1e9})
         # cfg4 (ii): triples N=4960 through transformers[1]
-        Bt = 4
+        Bt = 37
         qf = m.embed(Q[:Bt])
         ms = timed(lambda: m.score_features(1, qf), 2)
-        out.append({"config": "cfg4 20-way T=32 triples N=4960, B=4", "path": m.last_path(), "ms": ms, "windows_per_s": Bt / ms * 1e3})
+        out.append({"config": f"cfg4 20-way T=32 triples N=4960, B={Bt}", "path": m.last_path(), "ms": ms, "windows_per_s": Bt / ms * 1e3,
+                    "attention_tflops": 4 * 20 * 4960 * 4960 * 128 * Bt / ms / 1e9})
     except Exception as e:
         out.append({"config": "cfg4", "error": repr(e)})
     # cfg5: heatmap decode of 1024 frames
