@@ -179,12 +179,10 @@ ARX_API int arx_profile_enable(arx_handle *h, int32_t on);
 ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t reset);
 
 /* Debug knobs for kernel bring-up and tests.
- *  key 0: kernel-variant bit mask -- 1 K-major P operand (first-generation attention), 2 fp32 open-set head,
- *         4 fp32 CUDA-core linear layers, 8 first-generation attention kernel, 16 unfused projection (row-major
- *         projections + k_prep_k_img), 32 first-generation head pass, 64 timing only: skip the tuple build,
- *         128 second-generation attention kernel, 512 tuple build inside the projection GEMM epilogue,
- *         1024 one-tile-per-CTA GEMMs for the frame MLP, 2048 head projection on the caller's stream,
- *         4096 T=16 pair tuples on the tiled any-N kernels (set BEFORE the support set: it selects the operands built).
+ *  key 0: kernel-variant bit mask -- 4 fp32 CUDA-core linear layers in front of the tiled tcgen05 attention (T=16 pair
+ *         tuples leave their dedicated pipeline), 64 timing only: skip the tuple build, 1024 one-tile-per-CTA GEMMs for
+ *         the frame MLP, 2048 head projection on the caller's stream, 4096 T=16 pair tuples on the tiled any-N kernels.
+ *         Bits 4 and 4096 select which support operands are built: set them BEFORE the support set.
  *  key 1: (value != 0) arm a timeline trace of CTA 0 of the attention kernel.
  *  key 2: programmatic dependent launch for the score kernel chain.
  *  key 3: softmax-group scheduling of the attention kernel: < 0 the groups take turns on the MUFU phase

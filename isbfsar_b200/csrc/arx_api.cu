@@ -226,12 +226,11 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->fc1_w); cudaFree(h->fc1_b); cudaFree(h->fc2_w); cudaFree(h->fc2_b);
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     ArxTransformer &tr = h->tr[i];
-    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.q_slots); cudaFree(tr.bp_sums); cudaFree(tr.wp_ext);
+    cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.bp_sums); cudaFree(tr.wp_ext);
     cudaFree(tr.tup_packed);
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
-  cudaFree(h->wdr_img);
   for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2}) { cudaFree(L->w_img); cudaFree(L->bias); }
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); cudaFree(h->tr[i].tl_uab.w_img); cudaFree(h->tr[i].tl_uab.bias);
@@ -317,7 +316,6 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     UP(h->d1_w, w->d1_w, (size_t)256 * n2 * h->T); UP(h->d1_b, w->d1_b, 256);
     UP(h->d2_w, w->d2_w, 64 * 256); UP(h->d2_b, w->d2_b, 64);
     UP(h->d3_w, w->d3_w, 64); UP(h->d3_b, w->d3_b, 1);
-    if (h->cfg.force_path != 1 && (rc = arx_tc_prep_head_weights(h, st))) return rc;
   }
 #undef UP
   // tensor-core images of the linear layers (fp16, pre-swizzled); shapes outside these bounds stay on the fp32 kernels
@@ -499,7 +497,7 @@ static int support_scratch_reserve(arx_handle *h, int way, SupportScratch *out) 
 // linearity, graph replay), the tiled any-N tcgen05 kernels (arx_tcn.cu: T=32, triples, other T, LayerNorm affines
 // outside the static exp2 bound), or the fp32 CUDA-core kernels (forced, debug outputs, D != 128).
 static bool route_gen3(const arx_handle *h, const ArxTransformer &tr) {
-  return h->cfg.force_path != 1 && arx_tc_supported(h, tr) && h->T == 16 && tr.c == 2 && h->tc_linears && (h->tc_variant & 4096) == 0;
+  return h->cfg.force_path != 1 && arx_tc_supported(h, tr) && h->T == 16 && tr.c == 2 && h->tc_linears && (h->tc_variant & (4096 | 4)) == 0;
 }
 // LayerNorm affines outside the static bound: the ROWMAX variant of the tiled kernels is overflow-safe, but the fp16
 // operands of QK^T are no longer accurate enough there (measured on B200: gamma = 3 gives 5e-3 relative logit error
@@ -711,7 +709,7 @@ static ArxScoreGraph *score_graph_lookup(arx_handle *h, const ArxScoreGraphKey &
   h->graph_tick++;
   for (auto &g : h->graphs)
     if (g.key == key) { g.last_use = h->graph_tick; return &g; }
-  if (h->graphs.size() >= 8) {                     // evict the least recently used entry
+  if (h->graphs.size() >= 16) {                    // evict the least recently used entry
     size_t v = 0;
     for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[v].last_use) v = i;
     for (int i = 0; i < 2; ++i) if (h->graphs[v].exec[i]) cudaGraphExecDestroy(h->graphs[v].exec[i]);
@@ -748,6 +746,8 @@ template <class F> static int score_segment(arx_handle *h, ArxScoreGraph *g, int
   return ARX_OK;
 }
 }  // extern "C++"
+
+#define ARX_EP_UNSUPPORTED (-100)   /* internal: episode mode asked for a shape the batched kernels do not cover */
 
 // ---- scoring on the tiled any-N tcgen05 kernels (arx_tcn.cu) -----------------------------------------------------
 struct TcnWs {
@@ -849,81 +849,46 @@ static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float 
   return ARX_OK;
 }
 
-#define ARX_EP_UNSUPPORTED (-100)   /* internal: episode mode asked for a shape the batched kernels do not cover */
-// ep_way > 0: episode mode -- window b is scored against classes [b*ep_way, (b+1)*ep_way) of the support pool
-static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
-                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st, int ep_way = 0) {
-  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score: weights not loaded");
-  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score: support set not set");
-  if (n_windows == 0) return ARX_OK;
+// ---- the metric shape: T=16 pair tuples on the dedicated pipeline ---------------------------------------------------
+// frames -> fp16 image -> fc1 -> fc2 (persistent weight-resident GEMMs) -> K/V projection into the chunked fp32 buffer ->
+// tuple images (gather + LayerNorm + exp2 pre-scale) -> [join the support chain] -> cross-attention + distances ->
+// logits / argmax -> open-set head by linearity -> fc1 -> fc2 + fc3 + sigmoid.  Replayed as two CUDA graphs (before /
+// after the join) when the arguments recur.
+static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
+                      float *is_true_dev, int32_t *chosen_dev, cudaStream_t st, int ep_way) {
   const ArxTransformer &tr = h->tr[ti];
-  const bool from_frames = query_dev != nullptr;
-  const bool disc = is_true_dev != nullptr;
-  if (disc && (!h->cfg.has_discriminator || ti != 0 || tr.c != 2))
-    return arx_fail(h, ARX_ERR_INVALID, "score: the discriminator is sized for pair tuples of transformers[0] (model.py:283-285)");
+  const bool from_frames = query_dev != nullptr, disc = is_true_dev != nullptr;
   const int way = ep_way > 0 ? ep_way : h->way;
-  if (ep_way > 0 && (int64_t)ep_way * n_windows != h->way) return arx_fail(h, ARX_ERR_STATE, "score: episode pool does not match the batch");
-  const bool debug_out = probs || protos;
-  if (ep_way == 0 && !debug_out && route_tiled(h, tr)) {
-    int rc_t = workspace_wait(h, st);
-    if (rc_t) return rc_t;
-    if ((rc_t = score_tcn(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st))) return rc_t;
-    return score_done_record(h, st);
-  }
-  if (ep_way > 0 && !route_gen3(h, tr)) return ARX_EP_UNSUPPORTED;
-  if (!debug_out && !route_gen3(h, tr)) warn_fp32_fallback(h, ti);
-  bool use_tc = !debug_out && route_gen3(h, tr) && tr.ks_img != nullptr;
-  if (h->cfg.force_path == 2 && !use_tc && !debug_out)
-    return arx_fail(h, ARX_ERR_INVALID, "score: force_path=2 but the tcgen05 path does not support this shape (N=%d, bound=%g)", tr.N,
-                    (double)tr.softmax_bound);
-  const bool mode0 = use_tc && h->T == 16 && tr.c == 2;
-  const bool tc_head = use_tc && disc && arx_tc_head_supported(h, tr) && (h->tc_variant & 2) == 0;
-  const bool tuples32 = !use_tc || (disc && !tc_head) || !mode0;    // fp32 tuple tensors: fp32 path/head pass, generic epilogue
-  const bool tcl = use_tc && h->tc_linears && (h->tc_variant & 4) == 0;
-  // fused projection epilogue (Kq images + compact V projections): T=16 pairs, slot order, no fp32 tuple tensors needed
-  const bool fused_proj = tcl && mode0 && tr.table_in_gemm && arx_tc_slot_order(h, tr) && !tuples32 && (h->tc_variant & 16) == 0;
-  const bool head2 = fused_proj && tc_head && ti == 0 && h->tr[0].uc_img != nullptr && (h->tc_variant & 32) == 0;   // second-generation head pass
-  // default: persistent GEMM -> chunked fp32 projections, then the thread-per-tuple image kernel; the in-GEMM tuple
-  // epilogue (variant bit 9) and the older attention / head kernels (bits 3, 5, 7) read row-major projections
-  const bool split_proj = fused_proj && (h->tc_variant & (512 | 128 | 32 | 8)) == 0 && arx_tcp_supported(tr.tl_proj);
-  const int g_ld = (fused_proj && !split_proj) ? 2 * h->D : 2 * tr.c * h->D;      // row stride of G as the attention epilogues see it
-  const int g_voff = (fused_proj && !split_proj) ? 0 : tr.c * h->D;
+  if (disc && (ti != 0 || !tr.uc_img)) return arx_fail(h, ARX_ERR_STATE, "score: open-set head operands missing (set the support set again)");
   const bool big_batch = n_windows * h->T >= 128ll * 2 * h->sm_count;             // persistent GEMMs pay off from ~2 tiles per SM
-  const bool p_embed = tcl && big_batch && (h->tc_variant & 1024) == 0 && arx_tcp_supported(h->tl_fc1) && arx_tcp_supported(h->tl_fc2);
-  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, use_tc, tuples32, tcl, tc_head);
-  if (ep_way > 0 && !(use_tc && split_proj && (!disc || head2) && from_frames && chunk >= n_windows && (h->tc_variant & 128) == 0)) return ARX_EP_UNSUPPORTED;
-  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, use_tc, tuples32, tcl, tc_head);
-  size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
+  const bool p_embed = big_batch && (h->tc_variant & 1024) == 0 && arx_tcp_supported(h->tl_fc1) && arx_tcp_supported(h->tl_fc2);
+  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, true, false, true, disc);
+  if (ep_way > 0 && chunk < n_windows) return ARX_EP_UNSUPPORTED;
+  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, true, false, true, disc);
+  const size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
   int rc = arx_ws_reserve(h, sz.bytes + extra);
   if (rc) return rc;
-  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, use_tc, tuples32, tcl, tc_head);
+  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, true, false, true, disc);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
-  h->last_path = use_tc ? 2 : 1;
-  if ((rc = workspace_wait(h, st))) return rc;
+  h->last_path = 2;
   bool aux_pending = false;
   ArxScoreGraph *sg = nullptr;
-  bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;     // the default streams cannot be captured
-  if (capturable && graphs_enabled(h)) {              // a caller that is capturing this stream itself gets plain launches
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { (void)cudaGetLastError(); capturable = false; }
-  }
-  if (capturable && use_tc && split_proj && head2 && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf && graphs_enabled(h)) {
+  bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && graphs_enabled(h);     // the default streams cannot be captured
+  if (capturable && capture_id(st) != 0) capturable = false;      // a caller that is capturing this stream itself gets plain launches
+  if (capturable && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf) {
     ArxScoreGraphKey key;
     key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
-    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0); key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
+    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0);
+    key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
     sg = score_graph_lookup(h, key);
   }
+  const int f_nk = tr.tl_proj.nk, f_onehot = tr.table_in_gemm ? f_nk - 1 : -1;     // feature image: + one-hot sub-tile
+  const int g_ld = 2 * tr.c * h->D, g_voff = tr.c * h->D;
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
-    const int64_t n = std::min(chunk, n_windows - b0);
-    const float *FE;
+    const int64_t n = std::min(chunk, n_windows - b0), rows = n * h->T;
     if ((rc = prof_mark(h, 0, st))) return rc;
-    const int64_t rows = n * h->T;
-    const int f_nk = tr.tl_proj.nk, f_onehot = tr.table_in_gemm ? f_nk - 1 : -1;     // feature image: + one-hot sub-tile
     rc = score_segment(h, sg, 0, st, [&]() -> int {
-    int rc = ARX_OK;
-    if (tcl) {
-      // frame MLP + projection on tensor cores, activations chained as fp16 images
-      FE = nullptr;
+      int rc = ARX_OK;
       if (from_frames) {
         if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
         if (p_embed) {
@@ -933,95 +898,125 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
           if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
           if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
         }
-      } else {
-        if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, f_nk, f_onehot, st))) return rc;
-      }
+      } else if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, f_nk, f_onehot, st))) return rc;
       if ((rc = prof_mark(h, 1, st))) return rc;
-      if (fused_proj) {
-        int32_t slots[256];
-        arx_tc2_slot_table(slots);
-        const float alpha = (h->tc_variant & 64) ? -1.f : ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);   // bit 6: timing-only, skip the tuple build
-        if (split_proj) {
-          if ((rc = arx_tcp_linear_chunked(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, st))) return rc;
-          if (alpha > 0.f && (rc = arx_tuple_img(h, tr, w.G, 2 * tr.c * h->D / 32, n, w.kq_img, alpha, st))) return rc;
-        } else if ((rc = arx_tc_linear_proj16(h, tr.tl_proj, w.f_img, rows, w.kq_img, slots, tr.ln_g, tr.ln_b, alpha, w.G,
-                                              tr.table_in_gemm ? nullptr : tr.bp, 2 * tr.c * h->D, tr.bp_sums, st)))
-          return rc;
-        if (head2) {
-          // only the head pass reads these 32 columns: run them on a second stream, beside projection + attention
-          const bool aux = (h->tc_variant & 2048) == 0 && !h->prof_on && !sg;      // (a graph segment must end joined)
-          cudaStream_t us = st;
-          if (aux) {
-            if (!h->aux_stream) {
-              ARX_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
-              ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
-              ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_done, cudaEventDisableTiming));
-            }
-            us = h->aux_stream;
-            ARX_CUDA(h, cudaEventRecord(h->ev_aux_fork, st));
-            ARX_CUDA(h, cudaStreamWaitEvent(us, h->ev_aux_fork, 0));
+      const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
+      if ((rc = arx_tcp_linear_chunked(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, st))) return rc;
+      if ((rc = prof_mark(h, 2, st))) return rc;
+      if ((h->tc_variant & 64) == 0 && (rc = arx_tuple_img(h, tr, w.G, g_ld / 32, n, w.kq_img, alpha, st))) return rc;   // bit 6: timing only
+      if (disc) {
+        // only the head pass reads these 32 columns: run them on a second stream, beside the tuple build + attention
+        const bool aux = (h->tc_variant & 2048) == 0 && !h->prof_on && !sg;      // (a graph segment must end joined)
+        cudaStream_t us = st;
+        if (aux) {
+          if (!h->aux_stream) {
+            ARX_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+            ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
+            ARX_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_done, cudaEventDisableTiming));
           }
-          if ((rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows, w.uab, 32, tr.tcomp, h->T, us))) return rc;
-          if (aux) { ARX_CUDA(h, cudaEventRecord(h->ev_aux_done, us)); aux_pending = true; }
+          us = h->aux_stream;
+          ARX_CUDA(h, cudaEventRecord(h->ev_aux_fork, st));
+          ARX_CUDA(h, cudaStreamWaitEvent(us, h->ev_aux_fork, 0));
         }
-      } else if ((rc = arx_tc_linear_f32(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, 2 * tr.c * h->D, tr.table_in_gemm ? nullptr : tr.bp, h->T, st)))
-        return rc;
-    } else {
-      if (from_frames) {
-        if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, rows, w.H1, w.FE, st))) return rc;
-        FE = w.FE;
-      } else {
-        FE = qfeats_dev + b0 * h->T * h->F;
+        if ((rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows, w.uab, 32, tr.tcomp, h->T, us))) return rc;
+        if (aux) { ARX_CUDA(h, cudaEventRecord(h->ev_aux_done, us)); aux_pending = true; }
       }
-      if ((rc = prof_mark(h, 1, st))) return rc;
-      if ((rc = project_frames(h, tr, FE, rows, w.G, st))) return rc;
-    }
-    if ((rc = prof_mark(h, 2, st))) return rc;
-    if (tuples32 && (rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
-    if (use_tc && !fused_proj && (rc = arx_tc_prep_query(h, h->tr[ti], w.G, n, w.kq_img, mode0 && arx_tc_slot_order(h, tr), st))) return rc;
-    return ARX_OK;
+      return ARX_OK;
     });
     if (rc) return rc;
     if ((rc = support_wait(h, st))) return rc;                   // join the support chain (side stream) before its operands are read
-
     if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
-    const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
     rc = score_segment(h, sg, 1, st, [&]() -> int {
-    int rc = ARX_OK;
-    if (use_tc) {
-      if ((rc = arx_tc_attention(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, w.partial, logits_dev + b0 * way, ch,
-                                 h->tc_variant, g_ld, g_voff, split_proj, ep_way > 0, st)))
-        return rc;
+      int rc = ARX_OK;
+      if ((rc = arx_tc_attention(h, tr, w.kq_img, w.G, n, way, w.partial, logits_dev + b0 * way, ch, g_ld, g_voff, true, ep_way > 0, st))) return rc;
       if ((rc = prof_mark(h, 4, st))) return rc;
-      if (disc && head2) {
+      if (disc) {
         if (aux_pending) { ARX_CUDA(h, cudaStreamWaitEvent(st, h->ev_aux_done, 0)); aux_pending = false; }
         if ((rc = arx_tc2_head_launch(h, tr, w.kq_img, w.uab, n, ch, w.y_img, h->tl_d1.nk, ep_way, st))) return rc;
-      } else if (disc && tc_head && (rc = arx_tc_head_features(h, tr, w.kq_img, mode0 ? w.G : nullptr, w.Vq, n, way, ch, w.y, w.y_img,
-                                                               h->tl_d1.nk, g_ld, g_voff, st)))
-        return rc;
-      if (disc && !tc_head && (rc = arx_fp32_head_features(h, tr, w.Kq, w.Vq, n, way, w.Z, ch, w.y, st))) return rc;
-    } else {
-      if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
-                                   probs ? probs + b0 * way * NN : nullptr, protos ? protos + b0 * way * ND : nullptr, st)))
-        return rc;
-      if ((rc = prof_mark(h, 4, st))) return rc;
-    }
-    if (disc && w.y_img) {
-      if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
-      if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true_dev + b0, st))) return rc;
-    } else if (disc) {
-      const int K1 = tr.N * h->T;
-      if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
-      if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
-      if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
-    }
-    return ARX_OK;
+        if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true_dev + b0, st))) return rc;
+      }
+      return ARX_OK;
     });
     if (rc) return rc;
     if ((rc = prof_mark(h, 5, st))) return rc;
   }
   if (sg) sg->seen++;
+  return ARX_OK;
+}
+
+// ---- fp32 CUDA-core kernels: any shape, debug outputs (softmax scores, prototypes), forced path ---------------------
+static int score_fp32(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
+                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st) {
+  const ArxTransformer &tr = h->tr[ti];
+  const bool from_frames = query_dev != nullptr, disc = is_true_dev != nullptr;
+  const int way = h->way;
+  const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, false, true, false, false);
+  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr);
+  const size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
+  int rc = arx_ws_reserve(h, sz.bytes + extra);
+  if (rc) return rc;
+  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws);
+  int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
+  h->last_path = 1;
+  const int64_t NN = (int64_t)tr.N * tr.N, ND = (int64_t)tr.N * h->D;
+  for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
+    const int64_t n = std::min(chunk, n_windows - b0), rows = n * h->T;
+    if ((rc = prof_mark(h, 0, st))) return rc;
+    const float *FE;
+    if (from_frames) {
+      if ((rc = embed_frames(h, query_dev + b0 * h->T * h->J3, rows, w.H1, w.FE, st))) return rc;
+      FE = w.FE;
+    } else FE = qfeats_dev + b0 * h->T * h->F;
+    if ((rc = prof_mark(h, 1, st))) return rc;
+    if ((rc = project_frames(h, tr, FE, rows, w.G, st))) return rc;
+    if ((rc = prof_mark(h, 2, st))) return rc;
+    if ((rc = arx_fp32_build_tuples(h, tr, w.G, n, w.Kq, w.Vq, st))) return rc;
+    if ((rc = support_wait(h, st))) return rc;
+    if ((rc = prof_mark(h, 3, st))) return rc;
+    int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
+    if ((rc = arx_fp32_attention(h, tr, w.Kq, w.Vq, n, way, w.Z, w.partial, logits_dev + b0 * way, ch, disc ? w.y : nullptr,
+                                 probs ? probs + b0 * way * NN : nullptr, protos ? protos + b0 * way * ND : nullptr, st)))
+      return rc;
+    if ((rc = prof_mark(h, 4, st))) return rc;
+    if (disc) {
+      const int K1 = tr.N * h->T;
+      if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+      if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+      if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
+    }
+    if ((rc = prof_mark(h, 5, st))) return rc;
+  }
+  return ARX_OK;
+}
+
+// ep_way > 0: episode mode -- window b is scored against classes [b*ep_way, (b+1)*ep_way) of the support pool
+static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
+                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st, int ep_way = 0) {
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score: weights not loaded");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score: support set not set");
+  if (n_windows == 0) return ARX_OK;
+  const ArxTransformer &tr = h->tr[ti];
+  const bool disc = is_true_dev != nullptr;
+  if (disc && (!h->cfg.has_discriminator || ti != 0 || tr.c != 2))
+    return arx_fail(h, ARX_ERR_INVALID, "score: the discriminator is sized for pair tuples of transformers[0] (model.py:283-285)");
+  if (ep_way > 0 && (int64_t)ep_way * n_windows != h->way) return arx_fail(h, ARX_ERR_STATE, "score: episode pool does not match the batch");
+  const bool debug_out = probs || protos;
+  if (ep_way > 0 && (debug_out || !route_gen3(h, tr) || !tr.ks_img || !query_dev)) return ARX_EP_UNSUPPORTED;
+  int rc = workspace_wait(h, st);
+  if (rc) return rc;
+  if (!debug_out && route_gen3(h, tr) && tr.ks_img)
+    rc = score_gen3(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st, ep_way);
+  else if (!debug_out && route_tiled(h, tr))
+    rc = score_tcn(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st);
+  else if (h->cfg.force_path == 2 && !debug_out)
+    rc = arx_fail(h, ARX_ERR_INVALID, "score: force_path=2 but no tcgen05 path covers this shape (N=%d, D=%d)", tr.N, h->D);
+  else {
+    if (!debug_out) warn_fp32_fallback(h, ti);
+    rc = score_fp32(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, probs, protos, st);
+  }
+  if (rc) return rc;
   return score_done_record(h, st);
 }
 

@@ -372,21 +372,3 @@ int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq,
 
 // Open-set head input for an already-known winning class (model.py:323-324,196): softmax statistics and the
 // attention pass for class chosen[b] only, emitting y = diff.Wdr^T + bdr.
-int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float *Kq, const float *Vq, int64_t n_win, int way,
-                           float *Z, const int32_t *chosen, float *y, cudaStream_t st) {
-  const int N = tr.N, D = h->D;
-  const int nb = (N + TM - 1) / TM;
-  const float scale = 1.0f / sqrtf((float)D);
-  const size_t smem = (size_t)(2 * TK * (TM + TPAD) + TM * PS_LD + TM * DF_LD) * sizeof(float);
-  { const int rc_ = arx_func_smem(h, k_attend, (int)smem); if (rc_) return rc_; }
-  for (int64_t b0 = 0; b0 < n_win; b0 += 65535) {
-    int64_t nb_win = n_win - b0 < 65535 ? n_win - b0 : 65535;
-    dim3 g(nb, 1, (unsigned)nb_win);
-    k_colstats<<<g, 256, 0, st>>>(Kq + b0 * N * D, tr.ks, Z + b0 * way * N * 2, N, D, way, scale, chosen + b0);
-    ARX_LAUNCH_CHECK(h);
-    k_attend<<<g, 256, smem, st>>>(Kq + b0 * N * D, Vq + b0 * N * D, tr.ks, tr.vs, Z + b0 * way * N * 2, nullptr, chosen + b0,
-                                   y + b0 * N * h->T, h->dr_w, h->dr_b, h->T, nullptr, nullptr, N, D, way, scale);
-    ARX_LAUNCH_CHECK(h);
-  }
-  return ARX_OK;
-}

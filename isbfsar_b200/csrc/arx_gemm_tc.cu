@@ -15,13 +15,8 @@ using namespace ptx;
 
 constexpr uint32_t A_SUB = 128 * 128;       // 128 rows x 64 fp16
 constexpr int G_THREADS = 192;
-constexpr uint32_t PROJ_STG = 16 * 260 * 4;                 // one staged window of the fused projection epilogue (padded rows)
-constexpr uint32_t PROJ_EPI = 32768 + 4 * PROJ_STG + 1024;  // image + 4 staged windows + LayerNorm affine
 
-enum { OUT_IMG16 = 0, OUT_F32 = 1, OUT_SIGMOID_DOT = 2, OUT_PROJ16 = 3 };
-
-// internal slot order of the query tuples for the fused projection epilogue (frame pairs, -1 = pad)
-__constant__ int c_qslots[256];
+enum { OUT_IMG16 = 0, OUT_F32 = 1, OUT_SIGMOID_DOT = 2 };
 
 struct GemmParams {
   const __half *a_img;     // [m_tiles][nk][128 x 64]
@@ -43,13 +38,6 @@ struct GemmParams {
   // OUT_SIGMOID_DOT
   const float *w3, *b3;    // [BN], [1]
   float *out1;             // [M]
-  // OUT_PROJ16 (T=16 pair tuples): column tile 0 = K parts -> tuple gather + LayerNorm -> Kq images;
-  // column tile 1 = V parts -> fp32 [M][256]
-  __half *kq_img;          // [M/16] window images of 32 KB
-  const float *ln_g, *ln_b;
-  float alpha;
-  int table_ld;
-  const float *table_sums; // [T][2]: row sums of the table over the two K parts
 };
 
 template <int BN, int OUT, int NST>
@@ -59,7 +47,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
   constexpr uint32_t TM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr uint32_t BAR_OFF = (OUT == OUT_PROJ16 && PROJ_EPI > NST * STAGE) ? PROJ_EPI : NST * STAGE;
+  constexpr uint32_t BAR_OFF = NST * STAGE;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + BAR_OFF);     // full[NST], empty[NST], acc
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + BAR_OFF + (2 * NST + 1) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,124 +101,6 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
     mbar_wait(&bars[2 * NST], 0);
     tc_fence_after();
     float dot = 0.f;
-    if constexpr (OUT == OUT_PROJ16) {
-      if (nt == 0) {
-        // ---- K parts -> Kq images: K = LN(Gk1[i] + Gk2[j]) * alpha in fp16, internal slot order  (model.py:69-82).
-        // Warp w holds TMEM lanes 32w..32w+31 = the 16 frames of windows 2w and 2w+1.  Two rounds; in each, every warp
-        // stages ONE of its windows (16 x 256 fp32 frame projections, centred) in shared memory (the operand stages are
-        // idle now), then the 128 epilogue threads build the four staged windows one after the other with
-        // THREAD == TUPLE SLOT: the LayerNorm statistics are thread-local (no shuffles), the frame rows are read as
-        // broadcast / 2-way LDS.128, the 32 KB operand image is assembled in shared memory in its final swizzled
-        // layout and leaves with one bulk store.
-        uint8_t *img = smem;                                                   // 32 KB
-        float *stg = reinterpret_cast<float *>(smem + 32768);                 // [4 windows][16 frames][260]
-        float *gs = reinterpret_cast<float *>(smem + 32768 + 4 * PROJ_STG);   // gamma*alpha [128] | beta*alpha [128]
-        const int tid = warp * 32 + lane;
-        gs[tid] = __ldg(p.ln_g + tid) * p.alpha;
-        gs[128 + tid] = __ldg(p.ln_b + tid) * p.alpha;
-        // LayerNorm mean by linearity: mean(A_i + B_j) = mean(A_i) + mean(B_j), and every lane holds one whole frame
-        // row in its TMEM lane -- so the rows are stored CENTRED and a tuple only needs the sum of squares.
-        float sumA = 0.f, sumB = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem + lane_base + c0, v);
-          tmem_ld_wait();
-          float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            t0 += __uint_as_float(v[j]); t1 += __uint_as_float(v[j + 1]); t2 += __uint_as_float(v[j + 2]); t3 += __uint_as_float(v[j + 3]);
-          }
-          if (c0 < 128) sumA += (t0 + t1) + (t2 + t3); else sumB += (t0 + t1) + (t2 + t3);
-        }
-        const float mA = sumA * (1.0f / 128.0f), mB = sumB * (1.0f / 128.0f);
-        const int fi = c_qslots[2 * tid], fj = c_qslots[2 * tid + 1];
-        const bool live = fi >= 0;                                            // pad slots are zero rows
-        uint8_t *irow = img + (tid >> 3) * 1024 + (tid & 7) * 128;
-        const bool run = p.alpha > 0.f;                                       // alpha < 0: timing-only, skip the tuple build
-        for (int rd = 0; rd < 2; ++rd) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < 256; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_base + c0, v);
-            tmem_ld_wait();
-            if ((lane >> 4) == rd) {
-              const float m = c0 < 128 ? mA : mB;
-              float *dst = stg + warp * (PROJ_STG / 4) + (lane & 15) * 260 + c0;
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(v[4 * j]) - m, __uint_as_float(v[4 * j + 1]) - m,
-                                                                       __uint_as_float(v[4 * j + 2]) - m, __uint_as_float(v[4 * j + 3]) - m);
-            }
-          }
-          named_bar_sync(1, 128);
-#pragma unroll 1
-          for (int wn = 0; wn < 4; ++wn) {
-            const int64_t win = (int64_t)mt * 8 + wn * 2 + rd;
-            if (win * 16 >= p.M || !run) continue;                            // uniform over the CTA
-            const float4 *A = reinterpret_cast<const float4 *>(stg + wn * (PROJ_STG / 4) + (live ? fi : 0) * 260);
-            const float4 *B = reinterpret_cast<const float4 *>(stg + wn * (PROJ_STG / 4) + (live ? fj : 0) * 260 + 128);
-            uint64_t x[64];                                                   // the tuple row, zero-mean, as fp32 pairs
-            uint64_t q0 = 0ull, q1 = 0ull;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float4 a = A[c], b = B[c];
-              x[2 * c] = add2(pack2(a.x, a.y), pack2(b.x, b.y));
-              x[2 * c + 1] = add2(pack2(a.z, a.w), pack2(b.z, b.w));
-              q0 = fma2(x[2 * c], x[2 * c], q0);
-              q1 = fma2(x[2 * c + 1], x[2 * c + 1], q1);
-            }
-            float ql, qh;
-            unpack2(add2(q0, q1), ql, qh);
-            const float rstd = live ? rsqrtf((ql + qh) * (1.0f / 128.0f) + 1e-5f) : 0.f;
-            const uint64_t rr = pack2(rstd, rstd);
-            if (tid == 0) bulk_wait_read_all();                               // the previous image has left shared memory
-            named_bar_sync(2, 128);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              uint32_t h[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 g2 = *reinterpret_cast<const float2 *>(gs + c * 8 + 2 * k);
-                const float2 e2 = *reinterpret_cast<const float2 *>(gs + 128 + c * 8 + 2 * k);
-                float lo, hi;
-                unpack2(fma2(mul2(x[c * 4 + k], rr), pack2(g2.x, g2.y), pack2(e2.x, e2.y)), lo, hi);
-                const __half2 hh = __floats2half2_rn(lo, hi);
-                h[k] = live ? *reinterpret_cast<const uint32_t *>(&hh) : 0u;
-              }
-              *reinterpret_cast<uint4 *>(irow + (c >> 3) * 16384 + (((c & 7) ^ (tid & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(3, 128);
-            if (tid == 0) {
-              bulk_s2g(reinterpret_cast<uint8_t *>(p.kq_img) + (size_t)win * 32768, img, 32768);
-              bulk_commit();
-            }
-          }
-        }
-        if (tid == 0) bulk_wait_all();
-      } else {
-        // ---- V parts: fp32 [M][256] (bias and positional-encoding table folded in), read by the attention epilogues
-#pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem + lane_base + c0, v);
-          float4 tv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            tv[j] = p.table ? __ldg(reinterpret_cast<const float4 *>(p.table + (int64_t)(row % p.T) * p.table_ld + 256 + c0) + j)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-          tmem_ld_wait();
-          if (row < p.M) {
-            float *dst = p.c + row * 256 + c0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(__uint_as_float(v[4 * j]) + tv[j].x, __uint_as_float(v[4 * j + 1]) + tv[j].y,
-                                                                     __uint_as_float(v[4 * j + 2]) + tv[j].z, __uint_as_float(v[4 * j + 3]) + tv[j].w);
-          }
-        }
-      }
-    } else {
     if constexpr (OUT == OUT_IMG16) {
       if (p.onehot_sub >= 0 && nt == 0) {
         // extra K columns for the next GEMM: one-hot(frame position) twice (against the hi and lo halves of the
@@ -294,7 +164,6 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) dot = fmaf(x[j], __ldg(p.w3 + col0 + j), dot);
       }
-    }
     }
     if constexpr (OUT == OUT_SIGMOID_DOT) {
       if (row < p.M) p.out1[row] = 1.f / (1.f + expf(-(dot + __ldg(p.b3))));
@@ -391,7 +260,7 @@ __global__ void k_pad_bias(const float *__restrict__ b, int N, float *__restrict
 }
 
 template <int BN, int OUT, int NST = 2> int launch_gemm(arx_handle *h, const GemmParams &p, int n_tiles, cudaStream_t st) {
-  constexpr uint32_t body = (OUT == OUT_PROJ16 && PROJ_EPI > NST * (A_SUB + BN * 128)) ? PROJ_EPI : NST * (A_SUB + BN * 128);
+  constexpr uint32_t body = NST * (A_SUB + BN * 128);
   constexpr uint32_t smem = body + (2 * NST + 1) * 8 + 16 + 1024;
   auto kern = k_gemm_tc<BN, OUT, NST>;
   { const int rc_ = arx_func_smem(h, kern, (int)smem); if (rc_) return rc_; }
@@ -456,22 +325,6 @@ int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half 
 
 // Fused K/V projection for T=16 pair tuples: Kq images (tuple gather + LayerNorm + scale, internal slot order)
 // and the fp32 V projections [M][256], straight from the GEMM accumulator -- no `G` round trip.
-int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
-                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, float *table_sums,
-                         cudaStream_t st) {
-  if (L.BN != 256 || L.n_tiles != 2) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: needs a 512-column projection");
-  (void)table_sums;
-  if (table) return arx_fail(h, ARX_ERR_INVALID, "tc_linear_proj16: the positional table must come in through the one-hot K columns");
-  if (!(h->dev_init & ARX_INIT_QSLOTS)) {
-    ARX_CUDA(h, cudaMemcpyToSymbol(c_qslots, slots_host, 256 * sizeof(int)));
-    h->dev_init |= ARX_INIT_QSLOTS;
-  }
-  GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = L.nk; p.M = M; p.act = ARX_ACT_NONE; p.c = Gv; p.table = table; p.T = 16;
-  p.kq_img = kq_img; p.ln_g = ln_g; p.ln_b = ln_b; p.alpha = alpha; p.table_ld = table_ld; p.table_sums = table_sums;
-  return launch_gemm<256, OUT_PROJ16>(h, p, 2, st);
-}
-
 int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *out, cudaStream_t st) {
   k_table_sums<<<T, 64, 0, st>>>(table, ld, out);
   ARX_LAUNCH_CHECK(h);

@@ -30,7 +30,6 @@ struct ArxTransformer {
   float *ln_g = nullptr, *ln_b = nullptr;
   float ln_host[256] = {};  // host copy [gamma(128) | beta(128)] when D == 128: kernel-parameter operands of k_tuple_img
   int32_t *tuples = nullptr; // (N,c) int32, built on device
-  int32_t *q_slots = nullptr; // (128,2) internal padded-triangular order of the query tuples (T=16 pairs), -1 = pad
   // support operands, fp32 generic path: (W,N,D) each
   float *ks = nullptr, *vs = nullptr;
   // support operands, tcgen05 path: fp16 UMMA smem images, see arx_tc.cu
@@ -79,7 +78,6 @@ struct arx_handle {
   // discriminator (model.py:183-204)
   float *dr_w = nullptr, *dr_b = nullptr, *d1_w = nullptr, *d1_b = nullptr;
   float *d2_w = nullptr, *d2_b = nullptr, *d3_w = nullptr, *d3_b = nullptr;
-  __half *wdr_img = nullptr;   // dimensionality_reduction weight as a tcgen05 B operand
   ArxTcLinear tl_fc1, tl_fc2, tl_d1, tl_d2;
   bool tc_linears = false;     // frame MLP / projection / discriminator MLP run on tensor cores
   // support set
@@ -143,7 +141,7 @@ struct arx_handle {
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
   int attn_poly = 0;         // k_attn_tc3: every attn_poly-th register pair takes the FMA-pipe exp2 polynomial (0 = none; debug key 4)
   bool pdl = false;     // programmatic dependent launch for the arx_score kernel chain (debug key 2; measured: no gain, off by default)
-  int tc_variant = 0;   // debug: bit 0 selects the K-major P layout
+  int tc_variant = 0;   // debug key 0: kernel-variant bit mask (include/arx.h)
   std::string err;
 };
 
@@ -162,7 +160,7 @@ int arx_fail(arx_handle *h, int code, const char *fmt, ...);
   } while (0)
 
 int arx_ws_reserve(arx_handle *h, size_t bytes);
-enum ArxDevInit { ARX_INIT_PSLOTS = 1, ARX_INIT_QSLOTS = 2, ARX_INIT_SLOT_RANK = 4, ARX_INIT_FP32_ATTN = 8 };
+enum ArxDevInit { ARX_INIT_PSLOTS = 1 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size instead of once per launch
 template <class K> inline int arx_func_smem(arx_handle *h, K kern, int bytes) {
@@ -201,23 +199,13 @@ int arx_fp32_attention(arx_handle *h, const ArxTransformer &tr, const float *Kq,
                        int64_t n_win, int way, float *Z, float *partial, float *logits, int32_t *chosen,
                        float *y /* (n_win, N*T) or null */, float *probs, float *protos, cudaStream_t st);
 
-int arx_fp32_head_features(arx_handle *h, const ArxTransformer &tr, const float *Kq, const float *Vq, int64_t n_win, int way,
-                           float *Z, const int32_t *chosen, float *y, cudaStream_t st);
 
 // ---- tcgen05 kernels (arx_tc.cu) -------------------------------------------------
 bool arx_tc_supported(const arx_handle *h, const ArxTransformer &tr);
 int arx_tc_prep_support(arx_handle *h, ArxTransformer &tr, int way, cudaStream_t st);
 int arx_tc_support_build(arx_handle *h, ArxTransformer &tr, const float *G, int way, bool with_images, cudaStream_t st);
-int arx_tc_prep_query(arx_handle *h, ArxTransformer &tr, const float *G, int64_t n_win, __half *kq_img, bool slot_order, cudaStream_t st);
-bool arx_tc_slot_order(const arx_handle *h, const ArxTransformer &tr);
-int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                     int way, float *partial, float *logits, int32_t *chosen, int variant, int g_ld, int g_voff, bool g_chunked, bool episodes,
-                     cudaStream_t st);
-
-bool arx_tc_head_supported(const arx_handle *h, const ArxTransformer &tr);
-int arx_tc_prep_head_weights(arx_handle *h, cudaStream_t st);
-int arx_tc_head_features(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, const float *Vq, int64_t n_win,
-                         int way, const int32_t *chosen, float *y, __half *y_img, int y_nk, int g_ld, int g_voff, cudaStream_t st);
+int arx_tc_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way, float *partial,
+                     float *logits, int32_t *chosen, int g_ld, int g_voff, bool g_chunked, bool episodes, cudaStream_t st);
 
 // ---- tcgen05 GEMM (arx_gemm_tc.cu) ------------------------------------------------
 int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw, const float *bias, int N, int K, int BN, cudaStream_t st);
@@ -249,13 +237,6 @@ __host__ __device__ constexpr int arx_slot_j(int q) {   // == i for a pad slot
 static_assert(arx_slot_row_start(16) == 128, "slot layout must fill the 128-column tile exactly");
 
 void arx_tc2_slot_table(int32_t *out /* 256 */);
-int arx_tc2_attention_launch(arx_handle *h, const ArxTransformer &tr, const __half *kq_img, const float *G, int64_t n_win, int way,
-                             float *partial, int g_ld, int g_voff, cudaStream_t st);
-
-int arx_tc_linear_proj16(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, __half *kq_img, const int32_t *slots_host,
-                         const float *ln_g, const float *ln_b, float alpha, float *Gv, const float *table, int table_ld, float *table_sums,
-                         cudaStream_t st);
-
 int arx_tc_table_sums(arx_handle *h, const float *table, int T, int ld, float *out, cudaStream_t st);
 
 int arx_tc2_head_prepare_weights(arx_handle *h, ArxTransformer &tr, cudaStream_t st);
