@@ -538,7 +538,10 @@ def main():
         except Exception as e:                           # never lose the run over the launch mode
             sys.stderr.write(f"bench: whole-step graph unavailable ({e!r}); steps are launched eagerly\n")
             graph_step = None
-            torch.cuda.synchronize()
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
     if world > 1:                                        # every rank must take the same mode: the collective count differs
         ok = torch.tensor([1 if graph_step is not None else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -159,6 +159,17 @@ ARX_API int arx_score_host_submit(arx_handle *h, const float *query_host, int64_
                           float *logits_host, float *is_true_host, int32_t *chosen_host, int64_t *ticket);
 ARX_API int arx_score_host_wait(arx_handle *h, int64_t ticket);
 
+/* Resident streaming scorer: ActionRecognizer.inference (modules/ar/ar.py:30-84, called once per camera frame from
+ * main.py:111).  The handle keeps the sliding window on the device: arx_stream_push takes ONE new frame (3J floats, HOST),
+ * computes its MLP features and its position-independent K/V projections once, stores them in a ring of T frames, forms the
+ * window's per-frame projections as ring + positional table, scores the window against the current support set
+ * (transformers[0] + discriminator) and returns result_host[0..way) = softmax(logits) (ar.py:77), result_host[way] = is_true
+ * (ar.py:78).  *valid = 0 until seq_len frames have been pushed since the last reset (ar.py:43-44).  One H2D (the frame),
+ * one CUDA-graph launch and one D2H per call; synchronises the handle's internal stream.  Pair tuples only.
+ * arx_stream_reset forgets the window (previous_frames = []). */
+ARX_API int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, int32_t *valid);
+ARX_API int arx_stream_reset(arx_handle *h);
+
 /* MetrABS-style heatmap decode (modules/hpe/hpe.py:108-169 + main.py:103-105):
  *   logits_dev (B,8,8,32+8*32) fp32 -> poses_dev (B,3*n_out) fp32 root-centred,
  *   valid_dev (B) uint8 (0 where the reference returns None, hpe.py:152-153).

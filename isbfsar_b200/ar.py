@@ -45,13 +45,12 @@ class ActionRecognizer:
         self.way = args.way
         self.n_joints = args.n_joints if args.input_type == "skeleton" else 0
         self._support_key = None
-        # resident per-frame path: everything of a call runs on one explicit stream with preallocated buffers (pinned
-        # staging for the frame in, fixed query / score buffers, one pinned result out), so arx_score replays its
-        # kernel chain as CUDA graphs and a frame costs one small H2D, one D2H and one synchronisation
+        # resident per-frame path (arx_stream_push): the window lives on the device as a ring of per-frame projections;
+        # a frame costs one 360-byte H2D, one CUDA-graph replay and one (way+1)-float D2H
         self._stream = torch.cuda.Stream()
-        self._pin_in = None
-        self._q = None
-        self._outs = None
+        self._stream_ok = True           # resident streaming path available (pair tuples on the tiled tcgen05 kernels)
+        self._ring_count = 0             # frames the device ring holds (capped at seq_len)
+        self._pending_features = None
 
     # The support operands on the device are valid for exactly this content identity of the support set.  The host
     # app replaces the dict wholesale (main.py:321-333 `load`) and could edit tensors in place, so the key is built from
@@ -62,77 +61,99 @@ class ActionRecognizer:
         if t is None:
             return None
         if isinstance(t, torch.Tensor):
-            return (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+            return (t.data_ptr(), t._version, t.shape, t.device)
         return ("obj", id(t))
 
     def _current_key(self):
         return tuple((k, self._tkey(v.get("poses")), self._tkey(v.get("features"))) for k, v in self.support_set.items())
 
+    def _sync_support(self):
+        """Upload the support-side operands when the support set changed (ar.py:56-67); returns the class names.  A set
+        scored from poses gets its per-class features for the cache (ar.py:72-74) -- handed out by `_cache_features`
+        at the first full window, like the reference."""
+        names = list(self.support_set.keys())
+        key = self._current_key()
+        if key != self._support_key:
+            if all("features" in self.support_set[c] for c in names):
+                # ar.py:56-61 -- cached features (the zero padding up to `way` never reaches the scorer: only the real
+                # classes are labelled, ar.py:51)
+                self.ar.set_support(features=torch.stack([self.support_set[c]["features"] for c in names]))
+                self._pending_features = None
+            else:
+                self.ar.set_support(poses=torch.stack([self.support_set[c]["poses"] for c in names]))
+                self._pending_features = names
+            self._support_key = key
+        return names
+
+    def _cache_features(self):
+        if self._pending_features is not None:
+            feats = self.ar.support_features()
+            for i, c in enumerate(self._pending_features):                                 # ar.py:72-74
+                if c in self.support_set:
+                    self.support_set[c]["features"] = feats[i]
+            self._pending_features = None
+            self._support_key = self._current_key()
+
     def inference(self, data):
-        """ar.py:30-84.  data = {"sk": ndarray (3J,)}.  Returns (results, open_set_result, requires_focus)."""
+        """ar.py:30-84.  data = {"sk": ndarray (3J,)}.  Returns (results, open_set_result, requires_focus).
+
+        Resident path (arx_stream_push): the sliding window lives in a device ring of per-frame projections; a call
+        uploads ONE frame (360 B), replays one CUDA graph and reads back `way + 1` floats.  `previous_frames` is kept on
+        the host with the reference's list semantics; if the caller edits it, the ring is rebuilt from it."""
         if data is None or len(data) == 0:
             return {}, 0, {}
         if len(self.support_set) == 0:
             return {}, 0, {}
+        if not self._stream_ok:
+            return self._inference_batch(data)
+        frame = np.ascontiguousarray(np.asarray(data["sk"], dtype=np.float32).reshape(-1))
+        self.previous_frames.append({"sk": torch.from_numpy(frame.copy())})
+        few = len(self.previous_frames) < self.seq_len
+        if len(self.previous_frames) == self.seq_len + 1:
+            self.previous_frames = self.previous_frames[1:]
+        with torch.cuda.stream(self._stream):
+            names = self._sync_support()
+            try:
+                if self._ring_count + 1 < len(self.previous_frames) or (self._ring_count + 1 > len(self.previous_frames) and few):
+                    self.ar.stream_reset()                                                  # the caller edited previous_frames
+                    for f in self.previous_frames[:-1]:
+                        self.ar.stream_push(f["sk"].numpy())
+                    self._ring_count = len(self.previous_frames) - 1
+                probs, is_true, valid = self.ar.stream_push(frame)
+            except ValueError:
+                # shapes the resident path does not cover (see arx_stream_push): per-window batch path
+                self._stream_ok = False
+                self.previous_frames.pop()
+                return self._inference_batch(data)
+            self._ring_count = min(self._ring_count + 1, self.seq_len)
+            if few or not valid:
+                return {}, 0, {}
+            self._cache_features()
+        results = {}
+        for k, name in enumerate(names):
+            results[name] = probs[k]
+        return results, np.array(is_true, dtype=np.float32), self.requires_focus
+
+    def _inference_batch(self, data):
+        """The same call through the windowed scorer (one H2D of the frame, arx_score on the (1,T,3J) window)."""
         with torch.cuda.stream(self._stream):
             frame = {}
             for k, v in data.items():
                 host = torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)))
-                if self._pin_in is None or self._pin_in.shape != host.shape:
-                    self._stream.synchronize()
-                    self._pin_in = torch.empty(host.shape, dtype=torch.float32).pin_memory()
-                if k == "sk":
-                    self._stream.synchronize()                 # the previous frame's copy has left the staging buffer
-                    self._pin_in.copy_(host)
-                    dev = torch.empty(host.shape, dtype=torch.float32, device="cuda")
-                    dev.copy_(self._pin_in, non_blocking=True)
-                else:
-                    dev = host.cuda()
-                frame[k] = dev
+                frame[k] = host.cuda(non_blocking=False)
             self.previous_frames.append(frame)
             if len(self.previous_frames) < self.seq_len:
                 return {}, 0, {}
             elif len(self.previous_frames) == self.seq_len + 1:
                 self.previous_frames = self.previous_frames[1:]
-            rows = [f["sk"] for f in self.previous_frames]
-            if self._q is None or self._q.shape[1:] != (len(rows),) + tuple(rows[0].shape):
-                self._q = torch.empty((1, len(rows)) + tuple(rows[0].shape), dtype=torch.float32, device="cuda")
-            torch.stack(rows, out=self._q[0])                                             # (1,T,3J), fixed buffer
-
-            key = self._current_key()
-            if key != self._support_key:
-                names = list(self.support_set.keys())
-                if all("features" in self.support_set[c] for c in names):
-                    # ar.py:56-61 -- cached features (zero padding up to `way` never reaches the scorer: only
-                    # the real classes are labelled, ar.py:51)
-                    feats = torch.stack([self.support_set[c]["features"] for c in names])
-                    self.ar.set_support(features=feats)
-                else:
-                    poses = torch.stack([self.support_set[c]["poses"] for c in names])
-                    self.ar.set_support(poses=poses)
-                    feats = self.ar.support_features()
-                    for i, c in enumerate(names):                                           # ar.py:72-74
-                        self.support_set[c]["features"] = feats[i]
-                self._support_key = self._current_key()
-
-            n_cls = len(self.support_set)
-            if self._outs is None or self._outs[0].shape[1] != n_cls:
-                self._outs = (torch.empty((1, n_cls), dtype=torch.float32, device="cuda"),
-                              torch.empty((1, 1), dtype=torch.float32, device="cuda"),
-                              torch.empty((n_cls + 1,), dtype=torch.float32, device="cuda"),
-                              torch.empty((n_cls + 1,), dtype=torch.float32).pin_memory())
-            lo_buf, it_buf, res_dev, res_pin = self._outs
-            logits, is_true = self.ar.score(self._q, out=(lo_buf, it_buf))
-            res_dev[:n_cls] = torch.softmax(logits[0], dim=0)                              # ar.py:77
-            res_dev[n_cls:] = is_true[0]                                                   # ar.py:78
-            res_pin.copy_(res_dev, non_blocking=True)
-        self._stream.synchronize()
-        host_res = res_pin.numpy().copy()
-        few_shot_result, open_set_result = host_res[:n_cls], host_res[n_cls:]
-        results = {}
-        for k, name in enumerate(self.support_set.keys()):
-            results[name] = few_shot_result[k]
-        return results, open_set_result, self.requires_focus
+            q = torch.stack([f["sk"].cuda() for f in self.previous_frames]).unsqueeze(0)        # (1,T,3J)
+            names = self._sync_support()
+            self._cache_features()
+            logits, is_true = self.ar.score(q)
+            res = torch.cat([torch.softmax(logits[0], dim=0), is_true[0]]).cpu().numpy()          # ar.py:77-78
+        n_cls = len(names)
+        results = {name: res[k] for k, name in enumerate(names)}
+        return results, res[n_cls:], self.requires_focus
 
     def remove(self, flag):
         """ar.py:86-92"""

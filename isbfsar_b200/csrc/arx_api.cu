@@ -9,6 +9,7 @@
 #include <algorithm>
 
 static std::string g_create_err;
+extern "C" { static void stream_free(arx_handle *h); }
 
 int arx_fail(arx_handle *h, int code, const char *fmt, ...) {
   char buf[1024];
@@ -251,6 +252,7 @@ void arx_destroy(arx_handle *h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_support_done) cudaEventDestroy(h->ev_support_done);
   if (h->ev_score_done) cudaEventDestroy(h->ev_score_done);
+  stream_free(h);
   cudaFree(h->ws);
   cudaFree(h->zscratch);
   cudaFree(h->tcn_diag);
@@ -380,8 +382,11 @@ int arx_embed(arx_handle *h, const float *frames_dev, int64_t n_frames, float *f
 // stream may only wait on events recorded in the SAME capture, so every internal event remembers the capture it was
 // recorded in (0 = recorded eagerly) and waits follow these rules:
 //   same context (both eager, or same capture)      -> cudaStreamWaitEvent
-//   capturing now, event recorded eagerly before     -> the host waits for the event (cudaEventQuery poll: legal during
-//                                                       capture), the graph itself needs no dependency
+//   capturing now, event recorded eagerly before     -> no node: nothing inside a capture may wait on (or even query) outside
+//                                                       work; the work recorded eagerly before the capture began is ordered
+//                                                       before the graph by whoever launches it (arx_stream_push waits for
+//                                                       the support chain eagerly before it captures or replays; a caller
+//                                                       capturing arx_score alone must have synchronised after set_support)
 //   otherwise (event belongs to another capture)     -> nothing to wait for: replays are ordered by the launching stream
 static unsigned long long capture_id(cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -392,10 +397,6 @@ static unsigned long long capture_id(cudaStream_t st) {
 static int wait_event_cap(arx_handle *h, cudaStream_t waiter, cudaEvent_t ev, unsigned long long ev_cid, unsigned long long cur_cid) {
   if (ev_cid == cur_cid) {
     ARX_CUDA(h, cudaStreamWaitEvent(waiter, ev, 0));
-  } else if (cur_cid != 0 && ev_cid == 0) {
-    cudaError_t e;
-    while ((e = cudaEventQuery(ev)) == cudaErrorNotReady) {}
-    if (e != cudaSuccess) return arx_fail(h, ARX_ERR_CUDA, "event query failed: %s", cudaGetErrorString(e));
   }
   return ARX_OK;
 }
@@ -418,6 +419,7 @@ static int support_fork(arx_handle *h, cudaStream_t st, cudaStream_t *side) {
     if (rc) return rc;
   }
   h->support_cid = cid;
+  h->support_seq++;                 // a new support set is on its way: operands derived from the old one are stale
   *side = h->side_stream;
   return ARX_OK;
 }
@@ -532,7 +534,10 @@ static int support_from_features(arx_handle *h, const __half *f_img, const float
     if (h->D == 128) {
       if ((rc = arx_tc_support_build(h, tr, G, way, imgs, st))) return rc;      // tuples + LayerNorm + operand images, one launch
       if (imgs && i == 0 && h->tc_linears && h->cfg.has_discriminator && h->T == 16 && tr.c == 2 && (rc = arx_tc2_support_uc(h, tr, way, st))) return rc;
-      if (route_tiled(h, tr) && (rc = arx_tcn_prep_support(h, tr, way, i == 0 && h->cfg.has_discriminator && tr.c == 2 && h->T <= 32, st))) return rc;
+      if (route_tiled(h, tr)) {
+        if ((rc = arx_tcn_prep_support(h, tr, way, i == 0 && h->cfg.has_discriminator && tr.c == 2 && h->T <= 32, st))) return rc;
+        h->tiles_gen[i] = h->support_seq + 1;
+      }
     } else {
       if ((rc = arx_fp32_build_tuples(h, tr, G, way, tr.ks, tr.vs, st))) return rc;
     }
@@ -674,6 +679,7 @@ int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way, void *s
       if (i == 0 && h->tc_linears && h->cfg.has_discriminator && h->T == 16 && tr.c == 2 && (rc = arx_tc2_support_uc(h, tr, way, ss))) return rc;
     } else if (route_tiled(h, tr)) {
       if ((rc = arx_tcn_prep_support(h, tr, way, i == 0 && h->cfg.has_discriminator && tr.c == 2 && h->T <= 32, ss))) return rc;
+      h->tiles_gen[i] = h->support_seq + 1;
     }
   }
   h->way = way;
@@ -784,6 +790,33 @@ static TcnWs carve_tcn(arx_handle *h, const ArxTransformer &tr, int64_t n, int w
   return w;
 }
 
+// query tiles -> cross-attention -> logits / argmax -> open-set head, from the row-major per-frame projections w.G
+static int tcn_backend(arx_handle *h, const ArxTransformer &tr, const TcnWs &w, int64_t n, int way, bool tcl, float *logits, float *is_true,
+                       int32_t *ch, cudaStream_t st) {
+  const int ldg = 2 * tr.c * h->D;
+  int rc;
+  if ((rc = support_wait(h, st))) return rc;          // tup_packed and the class tiles come from the support chain
+  if ((rc = arx_tcn_prep_query(h, tr, w.G, ldg, n, w.kq, st))) return rc;
+  if ((rc = prof_mark(h, 3, st))) return rc;
+  if ((rc = arx_tcn_attention(h, tr, w.kq, w.G, ldg, n, way, w.partial, logits, ch, st))) return rc;
+  if ((rc = prof_mark(h, 4, st))) return rc;
+  if (is_true) {
+    if (tcl && ((int64_t)tr.N * h->T) % 64)       // fc1's K is padded to whole 64-column sub-tiles: the pad columns must be zero, not stale
+      ARX_CUDA(h, cudaMemsetAsync(w.y_img, 0, (size_t)((n + 127) / 128 * 128) * h->tl_d1.nk * 64 * sizeof(__half), st));
+    if ((rc = arx_tcn_head(h, tr, w.kq, w.G, ldg, n, ch, w.uab, w.y, w.y_img, tcl ? h->tl_d1.nk : 0, st))) return rc;
+    if (tcl) {
+      if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
+      if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true, st))) return rc;
+    } else {
+      const int K1 = tr.N * h->T;
+      if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+      if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
+      if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
+    }
+  }
+  return ARX_OK;
+}
+
 static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
                      float *is_true_dev, int32_t *chosen_dev, cudaStream_t st) {
   const ArxTransformer &tr = h->tr[ti];
@@ -824,26 +857,8 @@ static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float 
       if ((rc = project_frames(h, tr, FE, rows, w.G, st))) return rc;
     }
     if ((rc = prof_mark(h, 2, st))) return rc;
-    if ((rc = support_wait(h, st))) return rc;          // tup_packed and the class tiles come from the support chain
-    if ((rc = arx_tcn_prep_query(h, tr, w.G, ldg, n, w.kq, st))) return rc;
-    if ((rc = prof_mark(h, 3, st))) return rc;
     int32_t *ch = chosen_dev ? chosen_dev + b0 : chosen_ws;
-    if ((rc = arx_tcn_attention(h, tr, w.kq, w.G, ldg, n, way, w.partial, logits_dev + b0 * way, ch, st))) return rc;
-    if ((rc = prof_mark(h, 4, st))) return rc;
-    if (disc) {
-      if (tcl && ((int64_t)tr.N * h->T) % 64)       // fc1's K is padded to whole 64-column sub-tiles: the pad columns must be zero, not stale
-        ARX_CUDA(h, cudaMemsetAsync(w.y_img, 0, (size_t)((n + 127) / 128 * 128) * h->tl_d1.nk * 64 * sizeof(__half), st));
-      if ((rc = arx_tcn_head(h, tr, w.kq, w.G, ldg, n, ch, w.uab, w.y, w.y_img, tcl ? h->tl_d1.nk : 0, st))) return rc;
-      if (tcl) {
-        if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
-        if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true_dev + b0, st))) return rc;
-      } else {
-        const int K1 = tr.N * h->T;
-        if ((rc = arx_fp32_linear(h, w.y, K1, h->d1_w, K1, h->d1_b, w.h1, 256, n, 256, K1, ARX_ACT_RELU, nullptr, 1, st))) return rc;
-        if ((rc = arx_fp32_linear(h, w.h1, 256, h->d2_w, 256, h->d2_b, w.h2, 64, n, 64, 256, ARX_ACT_RELU, nullptr, 1, st))) return rc;
-        if ((rc = arx_fp32_linear(h, w.h2, 64, h->d3_w, 64, h->d3_b, is_true_dev + b0, 1, n, 1, 64, ARX_ACT_SIGMOID, nullptr, 1, st))) return rc;
-      }
-    }
+    if ((rc = tcn_backend(h, tr, w, n, way, tcl, logits_dev + b0 * way, is_true_dev ? is_true_dev + b0 : nullptr, ch, st))) return rc;
     if ((rc = prof_mark(h, 5, st))) return rc;
   }
   return ARX_OK;
@@ -1194,6 +1209,124 @@ int arx_score_host_wait(arx_handle *h, int64_t ticket) {
   // The slot's event may have been re-recorded for a newer request (submit never blocks the host): the copy-back
   // stream is in order, so that newer record completing implies this ticket's copies have landed too.
   ARX_CUDA(h, cudaEventSynchronize(h->hs_ev_done[ticket % ARX_HOST_DEPTH]));
+  return ARX_OK;
+}
+
+// ---- resident streaming scorer (ar.py:30-84) ------------------------------------------------------------------------
+static void stream_free(arx_handle *h) {
+  ArxStream &s = h->stream;
+  if (s.exec) cudaGraphExecDestroy(s.exec);
+  cudaFree(s.ring); cudaFree(s.slot); cudaFree(s.x_dev); cudaFree(s.out_dev); cudaFree(s.logits); cudaFree(s.is_true); cudaFree(s.chosen);
+  cudaFree(s.ws);
+  if (s.pin_in) cudaFreeHost(s.pin_in);
+  if (s.pin_out) cudaFreeHost(s.pin_out);
+  if (s.st) cudaStreamDestroy(s.st);
+  s = ArxStream();
+}
+
+int arx_stream_reset(arx_handle *h) {
+  if (!h) return ARX_ERR_INVALID;
+  ArxStream &s = h->stream;
+  s.count = 0;
+  if (s.ring) {
+    ARX_CUDA(h, cudaStreamSynchronize(s.st));
+    ARX_CUDA(h, cudaMemsetAsync(s.ring, 0, (size_t)h->T * 2 * h->tr[0].c * h->D * sizeof(float), s.st));
+    ARX_CUDA(h, cudaMemsetAsync(s.slot, 0, sizeof(int), s.st));
+  }
+  return ARX_OK;
+}
+
+int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, int32_t *valid) {
+  if (!h || !frame_host || !result_host) return arx_fail(h, ARX_ERR_INVALID, "stream_push: bad argument");
+  if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "stream_push: weights not loaded");
+  if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "stream_push: support set not set");
+  ArxTransformer &tr = h->tr[0];
+  const int way = h->way, NO = 2 * tr.c * h->D;
+  const bool disc = h->cfg.has_discriminator != 0, tcl = h->tc_linears;
+  if (h->cfg.force_path == 1 || !arx_tcn_supported(h, tr) || arx_tcn_needs_rowmax(tr) || tr.c != 2 || (disc && h->T > 32))
+    return arx_fail(h, ARX_ERR_INVALID, "stream_push: the resident streaming path covers pair tuples on the tiled tcgen05 kernels only");
+  ArxStream &s = h->stream;
+  int rc;
+  if (!s.ring) {
+    ARX_CUDA(h, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.ring), (size_t)h->T * NO * sizeof(float)));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.slot), sizeof(int)));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.x_dev), (size_t)h->J3 * sizeof(float)));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.is_true), sizeof(float)));
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.chosen), sizeof(int32_t)));
+    ARX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&s.pin_in), (size_t)h->J3 * sizeof(float)));
+    ARX_CUDA(h, cudaMemsetAsync(s.ring, 0, (size_t)h->T * NO * sizeof(float), s.st));
+    ARX_CUDA(h, cudaMemsetAsync(s.slot, 0, sizeof(int), s.st));
+    s.count = 0;
+  }
+  const bool stale = s.way != way || s.sgen != h->support_seq || s.wgen != h->weights_gen;
+  if (stale) {
+    ARX_CUDA(h, cudaStreamSynchronize(s.st));
+    if (s.exec) { cudaGraphExecDestroy(s.exec); s.exec = nullptr; }
+    s.seen = 0;
+    if (s.way != way) {
+      cudaFree(s.out_dev); cudaFree(s.logits);
+      if (s.pin_out) cudaFreeHost(s.pin_out);
+      s.out_dev = s.logits = s.pin_out = nullptr;
+      ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.out_dev), (size_t)(way + 1) * sizeof(float)));
+      ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.logits), (size_t)way * sizeof(float)));
+      ARX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&s.pin_out), (size_t)(way + 1) * sizeof(float)));
+    }
+    const size_t need = carve_tcn(h, tr, 1, way, false, disc, tcl, nullptr).bytes;
+    if (need > s.ws_bytes) {
+      cudaFree(s.ws);
+      s.ws = nullptr;
+      ARX_CUDA(h, cudaMalloc(&s.ws, need));
+      s.ws_bytes = need;
+    }
+    // the tiled class operands (the T=16 pair pipeline of arx_score builds its own images): from the fp32 tuple tensors
+    if (h->tiles_gen[0] != h->support_seq + 1) {
+      if ((rc = support_wait(h, s.st))) return rc;
+      if ((rc = arx_tcn_prep_support(h, tr, way, disc, s.st))) return rc;
+      h->tiles_gen[0] = h->support_seq + 1;
+    }
+    s.way = way; s.sgen = h->support_seq; s.wgen = h->weights_gen;
+  }
+  TcnWs w = carve_tcn(h, tr, 1, way, false, disc, tcl, s.ws);
+  auto body = [&]() -> int {
+    int rc;
+    ARX_CUDA(h, cudaMemcpyAsync(s.x_dev, s.pin_in, (size_t)h->J3 * sizeof(float), cudaMemcpyHostToDevice, s.st));
+    if ((rc = arx_stream_frame_launch(h, tr, s.x_dev, s.ring, s.slot, s.st))) return rc;
+    if ((rc = arx_stream_window_launch(h, tr, s.ring, w.G, s.slot, s.st))) return rc;
+    if ((rc = tcn_backend(h, tr, w, 1, way, tcl, s.logits, disc ? s.is_true : nullptr, s.chosen, s.st))) return rc;
+    if ((rc = arx_stream_out_launch(h, s.logits, disc ? s.is_true : nullptr, s.out_dev, way, s.st))) return rc;
+    ARX_CUDA(h, cudaMemcpyAsync(s.pin_out, s.out_dev, (size_t)(way + 1) * sizeof(float), cudaMemcpyDeviceToHost, s.st));
+    return ARX_OK;
+  };
+  memcpy(s.pin_in, frame_host, (size_t)h->J3 * sizeof(float));
+  if ((rc = support_wait(h, s.st))) return rc;            // eagerly, before any capture / replay: the support chain runs on its own stream
+  const bool prof = h->prof_on;
+  if (s.seen < 1 || prof || !graphs_enabled(h)) {
+    if ((rc = body())) return rc;                       // first sighting: eager (allocations, one-time initialisation)
+    s.seen++;
+  } else {
+    if (!s.exec) {
+      const int64_t l0 = h->launches;
+      ARX_CUDA(h, cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+      rc = body();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(s.st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess || !graph) return arx_fail(h, ARX_ERR_CUDA, "stream_push: capture failed: %s", cudaGetErrorString(e));
+      const cudaError_t e2 = cudaGraphInstantiate(&s.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e2 != cudaSuccess) { s.exec = nullptr; return arx_fail(h, ARX_ERR_CUDA, "stream_push: graph instantiation failed: %s", cudaGetErrorString(e2)); }
+      s.seen = (int)(h->launches - l0);                  // launches per frame (>= 1)
+      h->launches = l0;
+    }
+    ARX_CUDA(h, cudaGraphLaunch(s.exec, s.st));
+    h->launches += s.seen;
+  }
+  ARX_CUDA(h, cudaStreamSynchronize(s.st));
+  memcpy(result_host, s.pin_out, (size_t)(way + 1) * sizeof(float));
+  s.count++;
+  if (valid) *valid = s.count >= h->T ? 1 : 0;            // ar.py:43-44: nothing to report before seq_len frames were seen
+  h->last_path = 3;
   return ARX_OK;
 }
 

@@ -1,6 +1,6 @@
 // MetrABS-style heatmap decoder (kernel 5): soft-argmax over the 8x8(x8) logits, FOV test,
 // absolute reconstruction, homography undo, 32->n_out joint remap, root-centring.
-// HBM-bound: 73,728 B in / 360 B out per frame; one CTA per frame, lane == joint.
+// HBM-bound: 73,728 B in / 360 B out per frame; one WARP per frame, lane == joint.
 //
 // Reference restated (paths relative to the reference root):
 //   modules/hpe/hpe.py:108-146   softmax + soft-argmax (x<-w, y<-h, z<-d; 2-D head x255)
@@ -30,70 +30,61 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) k_decode(const float *__restrict__ logits, const float *__restrict__ expand,
-                                                int n_out, DecodeParams prm, float *__restrict__ poses,
-                                                uint8_t *__restrict__ valid) {
-  __shared__ float s_max[2][8][NJ];
-  __shared__ float s_sum[7][8][NJ];
-  const int64_t f = blockIdx.x;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const float *src = logits + f * (int64_t)(64 * CH);
-  // warp `wid` owns the 8 cells of image row h = wid; per cell: 1 two-D logit + 8 three-D logits per joint
-  float v2[8], v3[8][ND];
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const float *cell = src + (wid * 8 + w) * CH;
-    v2[w] = __ldg(cell + lane);
-#pragma unroll
-    for (int d = 0; d < ND; ++d) v3[w][d] = __ldg(cell + NJ + d * NJ + lane);
-  }
-  float m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    m2 = fmaxf(m2, v2[w]);
-#pragma unroll
-    for (int d = 0; d < ND; ++d) m3 = fmaxf(m3, v3[w][d]);
-  }
-  s_max[0][wid][lane] = m2;
-  s_max[1][wid][lane] = m3;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    m2 = fmaxf(m2, s_max[0][k][lane]);
-    m3 = fmaxf(m3, s_max[1][k][lane]);
-  }
+// ONE WARP PER FRAME, lane == joint.  The first version used one 256-thread CTA per frame: two block-wide barriers, then
+// seven warps exited while one ran the long dependent fp64 tail -- 16 % of HBM bandwidth.  Here a warp streams its frame
+// once (every load is a 128-byte coalesced row of 32 joints; four cells = 36 independent loads in flight per lane) with an
+// ONLINE softmax (running maximum, accumulators rescaled when it moves), so nothing is kept in registers across the frame
+// and no shared memory or barrier exists; the fp64 tail of one warp hides under the loads of the other resident warps.
+constexpr int WARPS_PER_CTA = 4;
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decode(const float *__restrict__ logits, const float *__restrict__ expand,
+                                                              int n_out, DecodeParams prm, float *__restrict__ poses,
+                                                              uint8_t *__restrict__ valid, int64_t n_frames) {
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (f >= n_frames) return;
+  const float *src = logits + f * (int64_t)(64 * CH) + lane;
   const float inv7 = 1.0f / 7.0f;
-  const float yh = (float)wid * inv7;          // linspace(0,1,8)[h]
-  float S2 = 0, X2 = 0, S3 = 0, X3 = 0, Z3 = 0;
+  // running maxima and sums: 2-D head (S, X, Y), 3-D head (S, X, Y, Z); coordinates are linspace(0,1,8)
+  float m2 = -1e30f, S2 = 0.f, X2 = 0.f, Y2 = 0.f;
+  float m3 = -1e30f, S3 = 0.f, X3 = 0.f, Y3 = 0.f, Z3 = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 4) {
+    float v[4][9];
 #pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    const float xw = (float)w * inv7;
-    float e = expf(v2[w] - m2);
-    S2 += e;
-    X2 = fmaf(e, xw, X2);
+    for (int u = 0; u < 4; ++u) {
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      float e3 = expf(v3[w][d] - m3);
-      S3 += e3;
-      X3 = fmaf(e3, xw, X3);
-      Z3 = fmaf(e3, (float)d * inv7, Z3);
+      for (int k = 0; k < 9; ++k) v[u][k] = __ldcs(src + (c0 + u) * CH + k * NJ);      // streamed once: evict-first
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cell = c0 + u;
+      const float yh = (float)(cell >> 3) * inv7, xw = (float)(cell & 7) * inv7;       // cell = h*8 + w; x <- w, y <- h
+      {
+        const float mn = fmaxf(m2, v[u][0]);
+        const float sc = __expf(m2 - mn), e = __expf(v[u][0] - mn);
+        S2 = fmaf(S2, sc, e); X2 = fmaf(X2, sc, e * xw); Y2 = fmaf(Y2, sc, e * yh);
+        m2 = mn;
+      }
+      float mc = v[u][1];
+#pragma unroll
+      for (int d = 1; d < ND; ++d) mc = fmaxf(mc, v[u][1 + d]);
+      const float mn = fmaxf(m3, mc);
+      const float sc = __expf(m3 - mn);
+      float es = 0.f, ez = 0.f;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const float e = __expf(v[u][1 + d] - mn);
+        es += e;
+        ez = fmaf(e, (float)d * inv7, ez);
+      }
+      S3 = fmaf(S3, sc, es); X3 = fmaf(X3, sc, es * xw); Y3 = fmaf(Y3, sc, es * yh); Z3 = fmaf(Z3, sc, ez);
+      m3 = mn;
     }
   }
-  s_sum[0][wid][lane] = S2; s_sum[1][wid][lane] = X2; s_sum[2][wid][lane] = S2 * yh;
-  s_sum[3][wid][lane] = S3; s_sum[4][wid][lane] = X3; s_sum[5][wid][lane] = S3 * yh; s_sum[6][wid][lane] = Z3;
-  __syncthreads();
-  if (wid != 0) return;
-  float t[7];
-#pragma unroll
-  for (int q = 0; q < 7; ++q) {
-    float a = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a += s_sum[q][k][lane];
-    t[q] = a;
-  }
   // lane == joint j
-  const double p2x = (double)(t[1] / t[0]) * 255.0, p2y = (double)(t[2] / t[0]) * 255.0;
-  const double r3x = (double)(t[4] / t[3]), r3y = (double)(t[5] / t[3]), r3z = (double)(t[6] / t[3]);
+  const double p2x = (double)(X2 / S2) * 255.0, p2y = (double)(Y2 / S2) * 255.0;
+  const double r3x = (double)(X3 / S3), r3y = (double)(Y3 / S3), r3z = (double)(Z3 / S3);
   const bool fov = p2x >= 18.0 && p2x <= 238.0 && p2y >= 18.0 && p2y <= 238.0;   // misc.py:218-220
   const unsigned fmask = __ballot_sync(0xffffffffu, fov);
   const bool ok = __popc(fmask) * 4 >= NJ;                       // hpe.py:152
@@ -131,23 +122,21 @@ __global__ void __launch_bounds__(256) k_decode(const float *__restrict__ logits
   const double qx = ax3 * prm.R[0] + ay3 * prm.R[3] + az3 * prm.R[6];
   const double qy = ax3 * prm.R[1] + ay3 * prm.R[4] + az3 * prm.R[7];
   const double qz = ax3 * prm.R[2] + ay3 * prm.R[5] + az3 * prm.R[8];
-  // joint remap (hpe.py:162-164): out[k] = sum_j q[j] * E[j][k]; root-centre on output joint 0 (main.py:103).
-  // Every lane forms the root with the same summation order, so the root row comes out exactly 0.
+  // joint remap (hpe.py:162-164): out[k] = sum_j q[j] * E[j][k]; root-centre on output joint 0 (main.py:103): the root is
+  // lane 0's own sum, broadcast -- so the root row comes out exactly 0.
   double r0x = 0, r0y = 0, r0z = 0;
-  for (int j = 0; j < NJ; ++j) {
-    const double e0 = (double)__ldg(expand + j * n_out);
-    r0x += __shfl_sync(0xffffffffu, qx, j) * e0;
-    r0y += __shfl_sync(0xffffffffu, qy, j) * e0;
-    r0z += __shfl_sync(0xffffffffu, qz, j) * e0;
-  }
   for (int k0 = 0; k0 < n_out; k0 += 32) {
     const int k = k0 + lane;
     double ox = 0, oy = 0, oz = 0;
+#pragma unroll 8
     for (int j = 0; j < NJ; ++j) {
       const double ej = (k < n_out) ? (double)__ldg(expand + j * n_out + k) : 0.0;
       ox += __shfl_sync(0xffffffffu, qx, j) * ej;
       oy += __shfl_sync(0xffffffffu, qy, j) * ej;
       oz += __shfl_sync(0xffffffffu, qz, j) * ej;
+    }
+    if (k0 == 0) {
+      r0x = __shfl_sync(0xffffffffu, ox, 0); r0y = __shfl_sync(0xffffffffu, oy, 0); r0z = __shfl_sync(0xffffffffu, oz, 0);
     }
     if (k < n_out) {
       float *o = poses + f * (int64_t)(n_out * 3) + k * 3;
@@ -173,7 +162,8 @@ int arx_decode_launch(arx_handle *h, const float *logits, int64_t n_frames, cons
   for (int i = 0; i < 9; ++i) { p.invK[i] = (float)inv[i]; p.R[i] = (double)R9[i]; }
   for (int64_t f0 = 0; f0 < n_frames; f0 += 1 << 30) {
     int64_t n = n_frames - f0 < (1 << 30) ? n_frames - f0 : (1 << 30);
-    k_decode<<<(unsigned)n, 256, 0, st>>>(logits + f0 * 64 * CH, expand, n_out, p, poses + f0 * n_out * 3, valid + f0);
+    k_decode<<<(unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(logits + f0 * 64 * CH, expand, n_out, p,
+                                                                                               poses + f0 * n_out * 3, valid + f0, n);
     ARX_LAUNCH_CHECK(h);
   }
   return ARX_OK;

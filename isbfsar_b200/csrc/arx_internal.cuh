@@ -66,6 +66,23 @@ struct ArxScoreGraph {
   uint64_t last_use = 0;
 };
 
+// Resident streaming scorer state (arx_stream_push): device ring of per-frame projections, its own workspace, stream,
+// pinned staging and the per-frame CUDA graph.
+struct ArxStream {
+  float *ring = nullptr;            // (T, 2cD) position-independent projections of the last T frames
+  int *slot = nullptr;              // device: ring slot the next frame goes to
+  float *x_dev = nullptr, *out_dev = nullptr, *logits = nullptr, *is_true = nullptr;
+  int32_t *chosen = nullptr;
+  float *pin_in = nullptr, *pin_out = nullptr;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  cudaStream_t st = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t sgen = 0, wgen = 0;      // support / weights generation the graph (and the tiled operands) were built for
+  int way = 0, seen = 0;
+  int64_t count = 0;                // frames pushed since the last reset
+};
+
 struct arx_handle {
   arx_config cfg{};
   int device = 0;
@@ -128,6 +145,7 @@ struct arx_handle {
   int last_path = 0;
   std::vector<ArxScoreGraph> graphs;     // small LRU cache (arx_score with recurring arguments)
   uint64_t graph_tick = 0, support_gen = 0, weights_gen = 0;
+  uint64_t support_seq = 0;              // increments whenever a new support set is set / imported
   int graphs_on = -1;                    // -1: from the environment (ARX_GRAPHS=0 disables), else 0/1 (debug key 5)
   // one-time per-DEVICE initialisation done by this handle (__constant__ tables, function attributes): kept per handle,
   // not process-wide, so a second handle on another GPU of the same process initialises its own device
@@ -136,6 +154,8 @@ struct arx_handle {
   std::unordered_map<const void *, int> smem_attr;   // dynamic shared-memory limit already set per kernel (saves a driver call per launch)
   float *zscratch = nullptr;        // softmax normaliser partials of the tiled attention kernel (arx_tcn.cu), per CTA
   size_t zscratch_bytes = 0;
+  ArxStream stream;
+  uint64_t tiles_gen[ARX_MAX_TRANSFORMERS] = {0, 0, 0, 0};   // support generation the tiled operands were built for (+1)
   int *tcn_diag = nullptr;          // watchdog record of the tiled attention kernel
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
@@ -267,6 +287,11 @@ int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_
                       float *partial, float *logits, int32_t *chosen, cudaStream_t st);
 int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
                  float *uab, float *y, __half *y_img, int y_nk, cudaStream_t st);
+
+// ---- streaming kernels (arx_stream.cu)
+int arx_stream_frame_launch(arx_handle *h, const ArxTransformer &tr, const float *x_dev, float *ring, int *slot_next, cudaStream_t st);
+int arx_stream_window_launch(arx_handle *h, const ArxTransformer &tr, const float *ring, float *G, int *slot_next, cudaStream_t st);
+int arx_stream_out_launch(arx_handle *h, const float *logits, const float *is_true, float *out, int way, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

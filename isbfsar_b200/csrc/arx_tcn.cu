@@ -700,7 +700,9 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
   { const int rc_ = arx_func_smem(h, kern, (int)SMEM_BYTES); if (rc_) return rc_; }
   kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
   ARX_LAUNCH_CHECK(h);
-  if (getenv("ARX_TCN_CHECK")) {            // bring-up: synchronise and report a watchdog record
+  cudaStreamCaptureStatus cs_ = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs_) != cudaSuccess) { (void)cudaGetLastError(); cs_ = cudaStreamCaptureStatusNone; }
+  if (getenv("ARX_TCN_CHECK") && cs_ == cudaStreamCaptureStatusNone) {            // bring-up: synchronise and report a watchdog record
     ARX_CUDA(h, cudaStreamSynchronize(st));
     int d[4] = {0, 0, 0, 0};
     ARX_CUDA(h, cudaMemcpy(d, h->tcn_diag, sizeof(d), cudaMemcpyDeviceToHost));

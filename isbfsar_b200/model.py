@@ -395,6 +395,28 @@ class TRXOS(nn.Module):
                                               self._stream()), h, "arx_score_episodes")
         return logits, is_true
 
+    def stream_push(self, frame):
+        """One camera frame (3J floats, host) through the resident streaming scorer (arx_stream_push): returns
+        (probs (way,) float32 numpy, is_true float, valid bool).  The sliding window lives on the device."""
+        import numpy as np
+        # per-frame fast path: the weights are re-validated (data_ptr / version of every parameter) whenever the support
+        # set is (re)processed and on every batch call, not on every camera frame
+        h = self._h if self._h is not None and self._weights_key is not None else self._ensure()
+        lib = _lib.load()
+        x = np.ascontiguousarray(np.asarray(frame, dtype=np.float32).reshape(-1))
+        if x.size != self.args.n_joints * 3:
+            raise ValueError("stream_push: frame must have 3*n_joints values")
+        way = lib.arx_support_way(h)
+        out = np.empty((way + 1,), dtype=np.float32)
+        valid = C.c_int32(0)
+        rc = lib.arx_stream_push(h, x.ctypes.data, out.ctypes.data, C.byref(valid))       # the handle carries its device
+        if rc:
+            _lib.check(rc, h, "arx_stream_push")
+        return out[:way], out[way:], bool(valid.value)
+
+    def stream_reset(self):
+        _lib.check(_lib.load().arx_stream_reset(self._ensure()), self._h, "arx_stream_reset")
+
     def score_features(self, ti, qfeats):
         """`transformers[ti](support, labels, queries)['logits']` from frame features (B,T,F)."""
         h = self._ensure()

@@ -582,38 +582,57 @@ def test_add_hook_scores_match_oracle_probs():
 
 
 def test_support_cache_round_trip_is_stable():
-    """ar.py:56-74: a support set scored from poses caches its features; after the set changes, the cached classes
-    re-enter through the features path.  Both routes must give the same logits within the tolerance."""
+    """ar.py:56-74: a support set scored from poses caches its features; afterwards (and after `load` of a saved set) the
+    classes re-enter through the features path.  Both routes must give the same result on the same window within the
+    tolerance, and both must match the reference logic."""
     from isbfsar_b200 import ActionRecognizer
+    from oracle.trx_oracle import ActionRecognizerOracle
     cfg = Cfg()
     sd = make_state_dict(cfg, 0)
-    ar = ActionRecognizer(Args(cfg), state_dict=torch_sd(sd))
     rng = np.random.default_rng(23)
     poses = (0.17 * rng.standard_normal((3, 16, 90))).astype(np.float32)
-    frames = (poses[1] + 0.05 * rng.standard_normal((16, 90))).astype(np.float32)
+    frames = (poses[1][np.arange(18) % 16] + 0.05 * rng.standard_normal((18, 90))).astype(np.float32)
+
+    def run(ar, fs):
+        out = None
+        for f in fs:
+            out = ar.inference({"sk": f})
+        return out
+
+    ar = ActionRecognizer(Args(cfg), state_dict=torch_sd(sd))
+    oa = ActionRecognizerOracle(cfg, sd)
     for i, n in enumerate(["a", "b"]):
-        ar.train({"flag": n, "data": {"poses": poses[i]}, "requires_focus": False})
-    for f in frames:
-        res1, os1, _ = ar.inference({"sk": f})              # poses route (no class has features yet)
+        inp = {"flag": n, "data": {"poses": poses[i]}, "requires_focus": False}
+        ar.train(inp)
+        oa.train(inp)
+    assert run(ar, frames[:15]) == ({}, 0, {})
+    assert not any("features" in v for v in ar.support_set.values())            # nothing is cached before the first full window
+    res1, os1, _ = ar.inference({"sk": frames[15]})                              # poses route
+    ro1, oo1, _ = run(oa, frames[:16])
     assert all("features" in v for v in ar.support_set.values())
-    res2, os2, _ = ar.inference({"sk": frames[-1]})          # same window again: nothing changed, operands reused
-    ar.previous_frames = ar.previous_frames[:-1]
-    ar._support_key = None                                   # force the cached-features route for the same classes
-    res3, os3, _ = ar.inference({"sk": frames[-1]})
+    for k in res1:
+        assert abs(res1[k] / ro1[k] - 1) < 2e-3
+    assert abs(os1[0] / oo1[0] - 1) < 1e-3
+    # a second recogniser that starts from the CACHED features (what main.py `load` restores): features route, same window
+    ar2 = ActionRecognizer(Args(cfg), state_dict=torch_sd(sd))
+    for n in ["a", "b"]:
+        ar2.support_set[n] = {k: v.clone() for k, v in ar.support_set[n].items()}
+        ar2.requires_focus[n] = False
+    res3, os3, _ = run(ar2, frames[:16])
     for k in res1:
         assert abs(res3[k] / res1[k] - 1) < 1e-3
     assert abs(os3[0] / os1[0] - 1) < 1e-3
-    # oracle on the same call sequence
-    oa = __import__("oracle.trx_oracle", fromlist=["ActionRecognizerOracle"]).ActionRecognizerOracle(cfg, sd)
-    for i, n in enumerate(["a", "b"]):
-        oa.train({"flag": n, "data": {"poses": poses[i]}, "requires_focus": False})
-    for f in frames:
-        ro, oo, _ = oa.inference({"sk": f})
-    for k in ro:
-        assert abs(res1[k] / ro[k] - 1) < 2e-3 and abs(res3[k] / ro[k] - 1) < 2e-3
+    # the window keeps sliding on both routes
+    for f in frames[16:]:
+        r1, _, _ = ar.inference({"sk": f})
+        r3, _, _ = ar2.inference({"sk": f})
+        ro, _, _ = oa.inference({"sk": f})
+        for k in r1:
+            assert abs(r1[k] / ro[k] - 1) < 2e-3 and abs(r3[k] / ro[k] - 1) < 2e-3
     # a third class arrives without features: the whole set goes back through the poses route (ar.py:62-67)
-    ar.train({"flag": "c", "data": {"poses": poses[2]}, "requires_focus": False})
-    oa.train({"flag": "c", "data": {"poses": poses[2]}, "requires_focus": False})
+    inp = {"flag": "c", "data": {"poses": poses[2]}, "requires_focus": False}
+    ar.train(inp)
+    oa.train(inp)
     r4, _, _ = ar.inference({"sk": frames[-1]})
     ro4, _, _ = oa.inference({"sk": frames[-1]})
     assert list(r4) == ["a", "b", "c"]
@@ -628,6 +647,44 @@ def test_support_cache_round_trip_is_stable():
     ro5, _, _ = oa.inference({"sk": frames[-1]})
     for k in r5:
         assert abs(r5[k] / ro5[k] - 1) < 2e-3
+    # the caller clears the window (previous_frames = []): the device ring follows
+    ar.previous_frames = []
+    oa.previous_frames = []
+    assert run(ar, frames[:15]) == ({}, 0, {})
+    r6, _, _ = ar.inference({"sk": frames[15]})
+    ro6, _, _ = run(oa, frames[:16])
+    for k in r6:
+        assert abs(r6[k] / ro6[k] - 1) < 2e-3
+
+
+def test_streaming_path_matches_windowed_scoring():
+    """arx_stream_push (ring of per-frame projections, one frame per call) against arx_score on the explicit windows."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    rng = np.random.default_rng(31)
+    support = (0.17 * rng.standard_normal((5, 16, 90))).astype(np.float32)
+    frames = np.concatenate([support[2] + 0.05 * rng.standard_normal((16, 90)), 0.17 * rng.standard_normal((24, 90))]).astype(np.float32)
+    m.set_support(poses=torch.from_numpy(support).cuda())
+    got = []
+    for i, f in enumerate(frames):
+        probs, is_true, valid = m.stream_push(f)
+        assert valid == (i >= 15)
+        if valid:
+            got.append(np.concatenate([probs, is_true]))
+    assert m.last_path() == 3
+    windows = np.stack([frames[i:i + 16] for i in range(len(frames) - 15)])
+    lo, it = TrxOracle(cfg, sd).score(support[None], np.arange(5)[None], windows)
+    ref = np.concatenate([torch.softmax(torch.from_numpy(lo), 1).numpy(), it], axis=1)
+    assert rel_err(np.array(got), ref).max() < 2e-3
+    assert np.array_equal(np.array(got)[:, :5].argmax(1), lo.argmax(1))
+    # a support-set change between frames is picked up; reset forgets the window
+    m.set_support(poses=torch.from_numpy(support[::-1].copy()).cuda())
+    probs, is_true, valid = m.stream_push(frames[0])
+    w = np.concatenate([frames[-15:], frames[:1]])[None]
+    lo2, it2 = TrxOracle(cfg, sd).score(support[::-1][None], np.arange(5)[None], w)
+    assert rel_err(probs, torch.softmax(torch.from_numpy(lo2), 1).numpy()[0]).max() < 2e-3
+    m.stream_reset()
+    assert m.stream_push(frames[0])[2] is False
 
 
 @pytest.mark.parametrize("b", [1, 28, 300])
