@@ -61,11 +61,12 @@ class ActionRecognizer:
         if t is None:
             return None
         if isinstance(t, torch.Tensor):
-            return (t.data_ptr(), t._version, t.shape, t.device)
+            return (t.data_ptr(), t._version, t.shape[0])
         return ("obj", id(t))
 
     def _current_key(self):
-        return tuple((k, self._tkey(v.get("poses")), self._tkey(v.get("features"))) for k, v in self.support_set.items())
+        tk = self._tkey
+        return tuple((k, tk(v.get("poses")), tk(v.get("features"))) for k, v in self.support_set.items())
 
     def _sync_support(self):
         """Upload the support-side operands when the support set changed (ar.py:56-67); returns the class names.  A set
@@ -111,24 +112,29 @@ class ActionRecognizer:
         few = len(self.previous_frames) < self.seq_len
         if len(self.previous_frames) == self.seq_len + 1:
             self.previous_frames = self.previous_frames[1:]
-        with torch.cuda.stream(self._stream):
-            names = self._sync_support()
-            try:
-                if self._ring_count + 1 < len(self.previous_frames) or (self._ring_count + 1 > len(self.previous_frames) and few):
-                    self.ar.stream_reset()                                                  # the caller edited previous_frames
-                    for f in self.previous_frames[:-1]:
-                        self.ar.stream_push(f["sk"].numpy())
-                    self._ring_count = len(self.previous_frames) - 1
-                probs, is_true, valid = self.ar.stream_push(frame)
-            except ValueError:
-                # shapes the resident path does not cover (see arx_stream_push): per-window batch path
-                self._stream_ok = False
-                self.previous_frames.pop()
-                return self._inference_batch(data)
-            self._ring_count = min(self._ring_count + 1, self.seq_len)
-            if few or not valid:
-                return {}, 0, {}
-            self._cache_features()
+        if self._current_key() != self._support_key:
+            with torch.cuda.stream(self._stream):              # support-set change: (re)process it on the recogniser's stream
+                names = self._sync_support()
+        else:
+            names = list(self.support_set.keys())
+        try:
+            if self._ring_count + 1 < len(self.previous_frames) or (self._ring_count + 1 > len(self.previous_frames) and few):
+                self.ar.stream_reset()                                                  # the caller edited previous_frames
+                for f in self.previous_frames[:-1]:
+                    self.ar.stream_push(f["sk"].numpy())
+                self._ring_count = len(self.previous_frames) - 1
+            probs, is_true, valid = self.ar.stream_push(frame)
+        except ValueError:
+            # shapes the resident path does not cover (see arx_stream_push): per-window batch path
+            self._stream_ok = False
+            self.previous_frames.pop()
+            return self._inference_batch(data)
+        self._ring_count = min(self._ring_count + 1, self.seq_len)
+        if few or not valid:
+            return {}, 0, {}
+        if self._pending_features is not None:
+            with torch.cuda.stream(self._stream):
+                self._cache_features()
         results = {}
         for k, name in enumerate(names):
             results[name] = probs[k]

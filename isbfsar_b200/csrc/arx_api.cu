@@ -1217,7 +1217,8 @@ static void stream_free(arx_handle *h) {
   ArxStream &s = h->stream;
   if (s.exec) cudaGraphExecDestroy(s.exec);
   cudaFree(s.ring); cudaFree(s.slot); cudaFree(s.x_dev); cudaFree(s.out_dev); cudaFree(s.logits); cudaFree(s.is_true); cudaFree(s.chosen);
-  cudaFree(s.ws);
+  cudaFree(s.ws); cudaFree(s.iota); cudaFree(s.y_all);
+  if (s.st2) { cudaStreamDestroy(s.st2); cudaEventDestroy(s.ev_fork); cudaEventDestroy(s.ev_join); }
   if (s.pin_in) cudaFreeHost(s.pin_in);
   if (s.pin_out) cudaFreeHost(s.pin_out);
   if (s.st) cudaStreamDestroy(s.st);
@@ -1243,7 +1244,8 @@ int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, 
   ArxTransformer &tr = h->tr[0];
   const int way = h->way, NO = 2 * tr.c * h->D;
   const bool disc = h->cfg.has_discriminator != 0, tcl = h->tc_linears;
-  if (h->cfg.force_path == 1 || !arx_tcn_supported(h, tr) || arx_tcn_needs_rowmax(tr) || tr.c != 2 || (disc && h->T > 32))
+  if (h->cfg.force_path == 1 || !arx_tcn_supported(h, tr) || arx_tcn_needs_rowmax(tr) || tr.c != 2 || (disc && h->T > 32) || h->J3 > 256 || h->H > 256 ||
+      h->F > 256)
     return arx_fail(h, ARX_ERR_INVALID, "stream_push: the resident streaming path covers pair tuples on the tiled tcgen05 kernels only");
   ArxStream &s = h->stream;
   int rc;
@@ -1271,8 +1273,20 @@ int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, 
       ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.out_dev), (size_t)(way + 1) * sizeof(float)));
       ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.logits), (size_t)way * sizeof(float)));
       ARX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&s.pin_out), (size_t)(way + 1) * sizeof(float)));
+      cudaFree(s.iota); cudaFree(s.y_all);
+      s.iota = nullptr; s.y_all = nullptr;
+      std::vector<int32_t> io(way);
+      for (int i = 0; i < way; ++i) io[i] = i;
+      ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.iota), (size_t)way * sizeof(int32_t)));
+      ARX_CUDA(h, cudaMemcpy(s.iota, io.data(), (size_t)way * sizeof(int32_t), cudaMemcpyHostToDevice));
+      ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&s.y_all), (size_t)way * tr.N * h->T * sizeof(float) + 256));
+      if (!s.st2) {
+        ARX_CUDA(h, cudaStreamCreateWithFlags(&s.st2, cudaStreamNonBlocking));
+        ARX_CUDA(h, cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+        ARX_CUDA(h, cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
+      }
     }
-    const size_t need = carve_tcn(h, tr, 1, way, false, disc, tcl, nullptr).bytes;
+    const size_t need = carve_tcn(h, tr, 1, way, false, disc, false, nullptr).bytes;      // fp32 head buffers (one window: matvec kernels)
     if (need > s.ws_bytes) {
       cudaFree(s.ws);
       s.ws = nullptr;
@@ -1287,15 +1301,31 @@ int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, 
     }
     s.way = way; s.sgen = h->support_seq; s.wgen = h->weights_gen;
   }
-  TcnWs w = carve_tcn(h, tr, 1, way, false, disc, tcl, s.ws);
+  TcnWs w = carve_tcn(h, tr, 1, way, false, disc, false, s.ws);
   auto body = [&]() -> int {
     int rc;
+    if ((rc = prof_mark(h, 0, s.st))) return rc;          // stage timers: 0 H2D + frame MLP/projection, 1 window + query tiles, 2 -, 3 attention, 4 head + D2H
     ARX_CUDA(h, cudaMemcpyAsync(s.x_dev, s.pin_in, (size_t)h->J3 * sizeof(float), cudaMemcpyHostToDevice, s.st));
     if ((rc = arx_stream_frame_launch(h, tr, s.x_dev, s.ring, s.slot, s.st))) return rc;
-    if ((rc = arx_stream_window_launch(h, tr, s.ring, w.G, s.slot, s.st))) return rc;
-    if ((rc = tcn_backend(h, tr, w, 1, way, tcl, s.logits, disc ? s.is_true : nullptr, s.chosen, s.st))) return rc;
-    if ((rc = arx_stream_out_launch(h, s.logits, disc ? s.is_true : nullptr, s.out_dev, way, s.st))) return rc;
+    if ((rc = prof_mark(h, 1, s.st))) return rc;
+    if ((rc = arx_stream_tiles_launch(h, tr, s.ring, s.slot, w.G, w.kq, s.st))) return rc;
+    if ((rc = prof_mark(h, 2, s.st))) return rc;
+    if ((rc = prof_mark(h, 3, s.st))) return rc;
+    const int ldg = 2 * tr.c * h->D;
+    // the open-set head input of EVERY class runs on a second stream beside the main attention launch (5 + 5 CTAs): the
+    // winner is only known afterwards, and at one window per call the kernels are all latency
+    if (disc) {
+      ARX_CUDA(h, cudaEventRecord(s.ev_fork, s.st));
+      ARX_CUDA(h, cudaStreamWaitEvent(s.st2, s.ev_fork, 0));
+      if ((rc = arx_tcn_head_all(h, tr, w.kq, w.G, ldg, way, s.iota, w.uab, s.y_all, s.st2))) return rc;
+      ARX_CUDA(h, cudaEventRecord(s.ev_join, s.st2));
+    }
+    if ((rc = arx_tcn_attention_partial(h, tr, w.kq, w.G, ldg, 1, way, w.partial, s.st))) return rc;
+    if ((rc = prof_mark(h, 4, s.st))) return rc;
+    if (disc) ARX_CUDA(h, cudaStreamWaitEvent(s.st, s.ev_join, 0));
+    if ((rc = arx_stream_tail_launch(h, tr, w.partial, s.y_all, w.h1, s.logits, s.out_dev, s.slot, way, s.st))) return rc;
     ARX_CUDA(h, cudaMemcpyAsync(s.pin_out, s.out_dev, (size_t)(way + 1) * sizeof(float), cudaMemcpyDeviceToHost, s.st));
+    if ((rc = prof_mark(h, 5, s.st))) return rc;
     return ARX_OK;
   };
   memcpy(s.pin_in, frame_host, (size_t)h->J3 * sizeof(float));

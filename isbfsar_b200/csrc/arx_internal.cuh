@@ -72,7 +72,10 @@ struct ArxStream {
   float *ring = nullptr;            // (T, 2cD) position-independent projections of the last T frames
   int *slot = nullptr;              // device: ring slot the next frame goes to
   float *x_dev = nullptr, *out_dev = nullptr, *logits = nullptr, *is_true = nullptr;
-  int32_t *chosen = nullptr;
+  int32_t *chosen = nullptr, *iota = nullptr;
+  float *y_all = nullptr;
+  cudaStream_t st2 = nullptr;       // the head of all classes runs beside the main attention launch
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float *pin_in = nullptr, *pin_out = nullptr;
   void *ws = nullptr;
   size_t ws_bytes = 0;
@@ -288,10 +291,16 @@ int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_
 int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
                  float *uab, float *y, __half *y_img, int y_nk, cudaStream_t st);
 
+int arx_tcn_head_all(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int way, const int32_t *iota,
+                     float *uab, float *y_all, cudaStream_t st);
+int arx_tcn_attention_partial(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
+                              float *partial, cudaStream_t st);
+
 // ---- streaming kernels (arx_stream.cu)
 int arx_stream_frame_launch(arx_handle *h, const ArxTransformer &tr, const float *x_dev, float *ring, int *slot_next, cudaStream_t st);
-int arx_stream_window_launch(arx_handle *h, const ArxTransformer &tr, const float *ring, float *G, int *slot_next, cudaStream_t st);
-int arx_stream_out_launch(arx_handle *h, const float *logits, const float *is_true, float *out, int way, cudaStream_t st);
+int arx_stream_tiles_launch(arx_handle *h, const ArxTransformer &tr, const float *ring, const int *slot_next, float *G, __half *kq, cudaStream_t st);
+int arx_stream_tail_launch(arx_handle *h, const ArxTransformer &tr, const float *partial, const float *y_all, float *h1, float *logits, float *out,
+                           int *slot_next, int way, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

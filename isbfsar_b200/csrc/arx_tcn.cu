@@ -61,6 +61,7 @@ struct AttnNParams {
   float *zscratch;          // [grid][2 unit parity][2 groups][2: Z | M][ns*128]
   int *diag;                // watchdog record (see mbar_wait_wd)
   int n_win, way, N, T, c, nq, ns, tab_ld, tab_off, tab_pstride, mode, L, y_nk;
+  int same_window;          // mode 1: every unit scores window 0 (against class chosen[u]); y row = u (streaming: the head of ALL classes at once)
 };
 
 // Watchdog wait: a protocol bug must not hang the GPU.  On a timeout (~1 s) the first thread to notice records
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
         int kq = 0;
         for (int ui = 0; ui < my_units; ++ui) {
           const int u = blockIdx.x + ui * gridDim.x;
-          const size_t win = head ? (size_t)u : (size_t)(u / p.way);
+          const size_t win = head ? (p.same_window ? 0 : (size_t)u) : (size_t)(u / p.way);
           const uint8_t *q0 = reinterpret_cast<const uint8_t *>(p.kq_img) + win * nq * IMG_BYTES;
           for (int pass = pass0; pass < 2; ++pass)
             for (int qp = 0; qp < nqp; ++qp, ++kq) {
@@ -391,8 +392,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
     int ke = 0;
     for (int ui = 0; ui < my_units; ++ui) {
       const int u = blockIdx.x + ui * gridDim.x;
-      const int win = head ? u : u / p.way;
-      const float *tb = p.tab + (size_t)win * p.T * p.tab_ld + p.tab_off + d;
+      const int win = head ? u : u / p.way;                    // output row
+      const float *tb = p.tab + (size_t)(head && p.same_window ? 0 : win) * p.T * p.tab_ld + p.tab_off + d;
       auto gather = [&](int qc, float (&v)[32]) {        // Vq of columns qc .. qc+31 (clamped: pad columns are masked later)
         const uint32_t tpl = __ldg(p.tup + min(qc + lane, p.N - 1));
 #pragma unroll
@@ -680,7 +681,8 @@ int arx_tcn_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, 
 
 static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, int n_units, cudaStream_t st) {
   const int grid = n_units < h->sm_count ? n_units : h->sm_count;
-  const size_t zbytes = (size_t)h->sm_count * 2 * 2 * 2 * tr.Npad * sizeof(float);
+  // two regions: a head launch may run beside a main launch on another stream (streaming path)
+  const size_t zhalf = (size_t)h->sm_count * 2 * 2 * 2 * tr.Npad, zbytes = 2 * zhalf * sizeof(float);
   if (h->zscratch_bytes < zbytes) {
     ARX_CUDA(h, cudaDeviceSynchronize());
     cudaFree(h->zscratch);
@@ -689,7 +691,7 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
     ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->zscratch), zbytes));
     h->zscratch_bytes = zbytes;
   }
-  p.zscratch = h->zscratch;
+  p.zscratch = h->zscratch + (p.mode == 1 ? zhalf : 0);
   if (!h->tcn_diag) {
     ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->tcn_diag), 8 * sizeof(int)));
     ARX_CUDA(h, cudaMemset(h->tcn_diag, 0, 8 * sizeof(int)));
@@ -715,6 +717,16 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
   return ARX_OK;
 }
 
+// squared-distance partials only (the streaming tail forms logits / argmax itself)
+int arx_tcn_attention_partial(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
+                              float *partial, cudaStream_t st) {
+  AttnNParams p{};
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.vct_tiles; p.tab = G; p.tup = tr.tup_packed; p.partial = partial;
+  p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
+  p.tab_ld = ldg; p.tab_off = tr.c * h->D; p.tab_pstride = h->D; p.mode = 0;
+  return tcn_launch(h, tr, p, (int)n_win * way, st);
+}
+
 // logits (n_win, way) and chosen (n_win) of transformer `tr` from the query tiles; G = row-major per-frame projections
 int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
                       float *partial, float *logits, int32_t *chosen, cudaStream_t st) {
@@ -727,6 +739,21 @@ int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_
   k_finish_n<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
+}
+
+// streaming: the head input of EVERY class of ONE window at once (y_all (way, N*L) fp32), so that it can run beside the main
+// attention launch instead of after it; `iota` = device array 0..way-1
+int arx_tcn_head_all(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int way, const int32_t *iota,
+                     float *uab, float *y_all, cudaStream_t st) {
+  if (tr.c != 2 || h->T > 32 || !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "tcn_head: pair tuples with T <= 32 only");
+  k_head_uab<<<(unsigned)h->T, 128, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, h->T, h->T);
+  ARX_LAUNCH_CHECK(h);
+  AttnNParams p{};
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.uc_tiles; p.tab = uab; p.tup = tr.tup_packed; p.chosen = iota;
+  p.y = y_all; p.y_img = nullptr; p.y_nk = 0; p.L = h->T;
+  p.n_win = way; p.way = 1; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
+  p.tab_ld = 64; p.tab_off = 0; p.tab_pstride = 32; p.mode = 1; p.same_window = 1;
+  return tcn_launch(h, tr, p, way, st);
 }
 
 // open-set head input y = dimensionality_reduction(diff of the winning class) (model.py:323-324,196), pair tuples

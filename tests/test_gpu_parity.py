@@ -681,7 +681,7 @@ def test_streaming_path_matches_windowed_scoring():
     m.set_support(poses=torch.from_numpy(support[::-1].copy()).cuda())
     probs, is_true, valid = m.stream_push(frames[0])
     w = np.concatenate([frames[-15:], frames[:1]])[None]
-    lo2, it2 = TrxOracle(cfg, sd).score(support[::-1][None], np.arange(5)[None], w)
+    lo2, it2 = TrxOracle(cfg, sd).score(support[::-1].copy()[None], np.arange(5)[None], w)
     assert rel_err(probs, torch.softmax(torch.from_numpy(lo2), 1).numpy()[0]).max() < 2e-3
     m.stream_reset()
     assert m.stream_push(frames[0])[2] is False
