@@ -213,6 +213,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def teardown(torch, dist, world, graphs=()):
+    """CUDA graphs that captured NCCL kernels must be destroyed before the communicator; a teardown that still hangs (seen
+    once: destroy_process_group never returned after graph replays) must not turn a finished measurement into a timeout:
+    the result line is already printed and flushed, so a watchdog ends the process with exit code 0."""
+    sys.stdout.flush()
+    if world > 1:
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+    for g in graphs:
+        try:
+            g.reset()
+        except Exception:
+            pass
+    try:
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+    if world > 1:
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        os._exit(0)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def timed_ms(torch, fn, reps, warm=2):
     for _ in range(warm):
@@ -447,8 +474,7 @@ def main():
                     "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
                     "data": "synthetic", "config": {"workload": "cfg3: " + r["workload"]}, "clocks": sampler.stop(), "cfg3": r}
             print(json.dumps(line), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        teardown(torch, dist, world)
         return
 
     cfg = Cfg()
@@ -511,51 +537,75 @@ def main():
     # ---- the step as ONE CUDA graph (set_support + score + all-gather): a step costs the host one graph launch, which is
     # what keeps 8 ranks sharing the box's cores in step; the library's own kernels are captured as plain launches
     # (arx_score notices the capture), the support chain's side stream forks and joins inside the graph.
-    graph_step = None
+    graph_steps = [None, None]
     launches_per_graph = 0
-    gat1 = ScoreGatherer(B, WAY, True, dev, depth=1)
+    gats = [ScoreGatherer(B, WAY, True, dev, depth=1) for _ in range(2)]
+    comm_stream = torch.cuda.Stream(device=dev)
+    step_no = [0]
     if not args.no_step_graph:
         try:
-            def body():
+            def body(i):
+                # graph i scores into buffer set i; the all-gather of the OTHER set (filled by the previous step) runs on a forked
+                # branch beside this step's kernels, so the collective is off the critical path; the last one is done eagerly
+                if world > 1:
+                    comm_stream.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(comm_stream):
+                        gats[1 - i].gather()
                 if not args.static_support:
                     model.set_support(poses=s_dev)
-                model.score(q_dev, out=gat1.out())
-                gat1.gather()
-            for _ in range(3):                       # warm-up of exactly this call sequence (allocations, one-time inits, NCCL)
-                body()
+                model.score(q_dev, out=gats[i].out())
+                if world > 1:
+                    torch.cuda.current_stream().wait_stream(comm_stream)
+            for _ in range(2):                       # warm-up of exactly this call sequence (allocations, one-time inits, NCCL)
+                body(0)
+                body(1)
             torch.cuda.synchronize()
-            l0 = model.launch_count()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
-                body()
-            launches_per_graph = model.launch_count() - l0
-            g.replay()
+            for i in range(2):
+                l0 = model.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                    body(i)
+                launches_per_graph = model.launch_count() - l0
+                graph_steps[i] = g
+            for i in range(2):
+                graph_steps[i].replay()
+            gats[1].gather()
             torch.cuda.synchronize()
-            res = gat1._result(0)[rank]
-            if not (torch.equal(res[0], ref_logits) and torch.equal(res[1], ref_true)):
-                raise RuntimeError("graph replay does not reproduce the eager scores")
-            graph_step = g
+            for i in range(2):
+                res = gats[i]._result(0)[rank]
+                if not (torch.equal(res[0], ref_logits) and torch.equal(res[1], ref_true)):
+                    raise RuntimeError("graph replay does not reproduce the eager scores")
         except Exception as e:                           # never lose the run over the launch mode
-            sys.stderr.write(f"bench: whole-step graph unavailable ({e!r}); steps are launched eagerly\n")
-            graph_step = None
+            sys.stderr.write(f"bench: whole-step graphs unavailable ({e!r}); steps are launched eagerly\n")
+            for g in graph_steps:
+                try:
+                    if g is not None:
+                        g.reset()
+                except Exception:
+                    pass
+            graph_steps = [None, None]
             try:
                 torch.cuda.synchronize()
             except Exception:
                 pass
-    if world > 1:                                        # every rank must take the same mode: the collective count differs
-        ok = torch.tensor([1 if graph_step is not None else 0], device=dev)
+    use_graph = graph_steps[0] is not None and graph_steps[1] is not None
+    if world > 1:                                        # every rank must take the same mode: the collective sequence differs
+        ok = torch.tensor([1 if use_graph else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            graph_step = None
+        use_graph = int(ok.item()) == 1
 
     def step():
-        if graph_step is not None:
-            graph_step.replay()
+        if use_graph:
+            graph_steps[step_no[0] & 1].replay()
+            step_no[0] += 1
         else:
             step_eager()
 
     def finish():
-        if graph_step is None:
+        if use_graph:
+            if world > 1:
+                gats[(step_no[0] - 1) & 1].gather()     # the last step's scores (every earlier gather rode inside the next graph)
+        else:
             drain()
 
     for _ in range(args.warmup):
@@ -594,7 +644,7 @@ def main():
     blocks = [first] + [timed_block(args.steps) for _ in range(repeats - 1)]
     total_ms = sum(blocks)
     n_steps_total = args.steps * repeats
-    launches = (model.launch_count() - l0) + (launches_per_graph * n_steps_total if graph_step is not None else 0)
+    launches = (model.launch_count() - l0) + (launches_per_graph * n_steps_total if use_graph else 0)
     clocks = sampler.stop()
 
     # ---- stage timers: the same steps launched eagerly with CUDA events between the stages (arx_profile_*)
@@ -757,7 +807,8 @@ def main():
                                           else "step = process support set (every rank, replicated poses) + score shard + all-gather scores; "
                                                "NCCL broadcast of the support tuple embeddings done and verified once before timing"),
                            "l2": "flushed between timed steps (256 MiB write)", "path": path,
-                           "launch": ("one CUDA graph per step (set_support + score + all-gather captured together)" if graph_step is not None
+                           "launch": ("one CUDA graph per step (set_support + score; with N>1 the all-gather of the previous step's scores rides on a forked "
+                                      "branch of the same graph, the last one is joined inside the last timed step)" if use_graph
                                       else "eager launches; the collective of batch k is joined after batch k+1 is scored"),
                            "timing": f"CUDA events per step on the launching stream, summed over {repeats} blocks of exactly {args.steps} steps "
                                      "(each block bracketed by barrier + synchronize); max over ranks; stage timers from a further pass of the same "
@@ -775,8 +826,7 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_per_kernel": per_kernel, "sustained": sustained,
                 "cfg3": cfg3, "other_configs": extras, "cpu_baseline": cpu, "parity_check_max_rel_err": err}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown(torch, dist, world, [g for g in graph_steps if g is not None])
 
 
 if __name__ == "__main__":
