@@ -180,6 +180,19 @@ ARX_API int arx_decode_heatmaps(arx_handle *h, const float *logits_dev, int64_t 
                         const float *new_K_host9, const float *homo_inv_host9,
                         float *poses_dev, uint8_t *valid_dev, void *stream);
 
+/* Same decode with a camera PER FRAME: new_K_dev / homo_inv_dev are (n_frames,3,3) fp32 device arrays.  This is the
+ * test-time-augmentation call shape (hpe.py:88-93, misc.py:310-327): every augmented crop of a camera frame has its own
+ * scaled intrinsics and its own rotation/flip to undo. */
+ARX_API int arx_decode_heatmaps_cams(arx_handle *h, const float *logits_dev, int64_t n_frames, const float *expand_dev, int32_t n_out,
+                             const float *new_K_dev, const float *homo_inv_dev, float *poses_dev, uint8_t *valid_dev, void *stream);
+
+/* MetrABS heads that produce those logits: Linear(1280 -> 288) applied to every cell of the (8,8,1280) backbone feature map
+ * (modules/hpe/setup/4_create_heads_onnx.py:7-16; the reference runs it as a TensorRT fp16 engine, hpe.py:106).  tcgen05 GEMM,
+ * fp16 operands / fp32 accumulate.  weight (288,1280) and bias (288) fp32, host or device; feats_dev (n_frames,8,8,1280) fp32 ->
+ * logits_dev (n_frames,8,8,288) fp32, the input of arx_decode_heatmaps. */
+ARX_API int arx_heads_load(arx_handle *h, const float *weight, const float *bias, int32_t on_device, void *stream);
+ARX_API int arx_heads_forward(arx_handle *h, const float *feats_dev, int64_t n_frames, float *logits_dev, void *stream);
+
 /* Stage timers for roofline reporting: CUDA events recorded on the caller's stream around the
  * stages of arx_score (0 frame embedding MLP, 1 per-frame K/V projection, 2 tuple build + LayerNorm,
  * 3 cross-attention + distances, 4 open-set head).  arx_profile_read synchronises the events,

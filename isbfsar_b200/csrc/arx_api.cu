@@ -232,7 +232,7 @@ void arx_destroy(arx_handle *h) {
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
-  for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2}) { cudaFree(L->w_img); cudaFree(L->bias); }
+  for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2, &h->tl_heads}) { cudaFree(L->w_img); cudaFree(L->bias); }
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); cudaFree(h->tr[i].tl_uab.w_img); cudaFree(h->tr[i].tl_uab.bias);
     cudaFree(h->tr[i].wc); cudaFree(h->tr[i].tcomp);
@@ -1358,6 +1358,51 @@ int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, 
   if (valid) *valid = s.count >= h->T ? 1 : 0;            // ar.py:43-44: nothing to report before seq_len frames were seen
   h->last_path = 3;
   return ARX_OK;
+}
+
+// ---- MetrABS heads: Linear(1280 -> 288) over the (8,8) feature map (modules/hpe/setup/4_create_heads_onnx.py:7-16) -----
+int arx_heads_load(arx_handle *h, const float *weight, const float *bias, int32_t on_device, void *stream) {
+  if (!h || !weight || !bias) return arx_fail(h, ARX_ERR_INVALID, "heads_load: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = 288, K = 1280;
+  float *w = nullptr, *b = nullptr;
+  ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&w), (size_t)N * K * sizeof(float)));
+  ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&b), (size_t)N * sizeof(float)));
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaError_t e = cudaMemcpyAsync(w, weight, (size_t)N * K * sizeof(float), kind, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b, bias, (size_t)N * sizeof(float), kind, st);
+  int rc = e == cudaSuccess ? arx_tc_linear_prepare(h, h->tl_heads, w, K, b, N, K, 256, st) : arx_fail(h, ARX_ERR_CUDA, "heads_load: %s", cudaGetErrorString(e));
+  cudaStreamSynchronize(st);
+  cudaFree(w);
+  cudaFree(b);
+  if (rc == ARX_OK) h->heads_loaded = true;
+  return rc;
+}
+
+int arx_heads_forward(arx_handle *h, const float *feats_dev, int64_t n_frames, float *logits_dev, void *stream) {
+  if (!h || !feats_dev || !logits_dev || n_frames < 0) return arx_fail(h, ARX_ERR_INVALID, "heads_forward: bad argument");
+  if (!h->heads_loaded) return arx_fail(h, ARX_ERR_STATE, "heads_forward: heads weights not loaded");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = 1280, N = 288, nk = h->tl_heads.nk;
+  int rc = workspace_wait(h, st);
+  if (rc) return rc;
+  const int64_t chunk = 512;                                  // frames per pass: 32768 rows, 84 MB of fp16 operand image
+  if ((rc = arx_ws_reserve(h, (size_t)chunk * 64 * nk * 64 * sizeof(__half) + 256))) return rc;
+  __half *img = static_cast<__half *>(h->ws);
+  for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int64_t rows = std::min(chunk, n_frames - f0) * 64;
+    if ((rc = arx_tc_rows_to_img(h, feats_dev + f0 * 64 * K, K, K, rows, img, nk, -1, st))) return rc;
+    if ((rc = arx_tc_linear_f32(h, h->tl_heads, img, nk, rows, logits_dev + f0 * 64 * N, N, nullptr, 1, st, true))) return rc;
+  }
+  return score_done_record(h, st);
+}
+
+int arx_decode_heatmaps_cams(arx_handle *h, const float *logits_dev, int64_t n_frames, const float *expand_dev, int32_t n_out,
+                             const float *new_K_dev, const float *homo_inv_dev, float *poses_dev, uint8_t *valid_dev, void *stream) {
+  if (!h || !logits_dev || !expand_dev || !new_K_dev || !homo_inv_dev || !poses_dev || !valid_dev || n_frames < 0 || n_out < 1)
+    return arx_fail(h, ARX_ERR_INVALID, "decode_heatmaps_cams: bad argument");
+  return arx_decode_launch(h, logits_dev, n_frames, expand_dev, n_out, nullptr, nullptr, poses_dev, valid_dev, static_cast<cudaStream_t>(stream),
+                           new_K_dev, homo_inv_dev);
 }
 
 int arx_decode_heatmaps(arx_handle *h, const float *logits_dev, int64_t n_frames, const float *expand_dev, int32_t n_out,

@@ -39,10 +39,24 @@ constexpr int WARPS_PER_CTA = 4;
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decode(const float *__restrict__ logits, const float *__restrict__ expand,
                                                               int n_out, DecodeParams prm, float *__restrict__ poses,
-                                                              uint8_t *__restrict__ valid, int64_t n_frames) {
+                                                              uint8_t *__restrict__ valid, int64_t n_frames,
+                                                              const float *__restrict__ Ks, const float *__restrict__ Rs) {
   const int lane = threadIdx.x & 31;
   const int64_t f = (int64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
   if (f >= n_frames) return;
+  if (Ks) {
+    // per-frame camera (test-time augmentation, hpe.py:88-93: every augmented crop has its own intrinsics and its own
+    // rotation/flip to undo): inverse intrinsics by the adjugate in double, rounded to float32 like np.linalg.inv(float32)
+    double a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = (double)__ldg(Ks + f * 9 + i);
+    const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+    const double inv[9] = {(a[4] * a[8] - a[5] * a[7]) / det, (a[2] * a[7] - a[1] * a[8]) / det, (a[1] * a[5] - a[2] * a[4]) / det,
+                           (a[5] * a[6] - a[3] * a[8]) / det, (a[0] * a[8] - a[2] * a[6]) / det, (a[2] * a[3] - a[0] * a[5]) / det,
+                           (a[3] * a[7] - a[4] * a[6]) / det, (a[1] * a[6] - a[0] * a[7]) / det, (a[0] * a[4] - a[1] * a[3]) / det};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { prm.invK[i] = (float)inv[i]; prm.R[i] = (double)__ldg(Rs + f * 9 + i); }
+  }
   const float *src = logits + f * (int64_t)(64 * CH) + lane;
   const float inv7 = 1.0f / 7.0f;
   // running maxima and sums: 2-D head (S, X, Y), 3-D head (S, X, Y, Z); coordinates are linspace(0,1,8)
@@ -148,9 +162,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_decode(const float *__re
 }  // namespace
 
 int arx_decode_launch(arx_handle *h, const float *logits, int64_t n_frames, const float *expand, int n_out, const float *K9,
-                      const float *R9, float *poses, uint8_t *valid, cudaStream_t st) {
+                      const float *R9, float *poses, uint8_t *valid, cudaStream_t st, const float *Ks_dev, const float *Rs_dev) {
   if (n_frames == 0) return ARX_OK;
-  DecodeParams p;
+  DecodeParams p{};
+  if (Ks_dev) {
+    for (int64_t f0 = 0; f0 < n_frames; f0 += 1 << 30) {
+      int64_t n = n_frames - f0 < (1 << 30) ? n_frames - f0 : (1 << 30);
+      k_decode<<<(unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(logits + f0 * 64 * CH, expand, n_out, p,
+                                                                                                 poses + f0 * n_out * 3, valid + f0, n, Ks_dev + f0 * 9,
+                                                                                                 Rs_dev + f0 * 9);
+      ARX_LAUNCH_CHECK(h);
+    }
+    return ARX_OK;
+  }
   // inverse of the (float32) intrinsics via the adjugate in double, rounded to float32 like np.linalg.inv(float32)
   double a[9];
   for (int i = 0; i < 9; ++i) a[i] = (double)K9[i];
@@ -163,7 +187,7 @@ int arx_decode_launch(arx_handle *h, const float *logits, int64_t n_frames, cons
   for (int64_t f0 = 0; f0 < n_frames; f0 += 1 << 30) {
     int64_t n = n_frames - f0 < (1 << 30) ? n_frames - f0 : (1 << 30);
     k_decode<<<(unsigned)((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, st>>>(logits + f0 * 64 * CH, expand, n_out, p,
-                                                                                               poses + f0 * n_out * 3, valid + f0, n);
+                                                                                               poses + f0 * n_out * 3, valid + f0, n, nullptr, nullptr);
     ARX_LAUNCH_CHECK(h);
   }
   return ARX_OK;

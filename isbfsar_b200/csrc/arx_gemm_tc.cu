@@ -306,9 +306,9 @@ int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, 
 
 // A.W^T (+ table[row % T]) -> fp32 row-major
 int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table, int T,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool with_bias) {
   GemmParams p{};
-  p.a_img = a_img; p.w_img = L.w_img; p.bias = nullptr; p.nk = L.nk; p.a_nk = a_nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
+  p.a_img = a_img; p.w_img = L.w_img; p.bias = with_bias ? L.bias : nullptr; p.nk = L.nk; p.a_nk = a_nk; p.M = M; p.act = ARX_ACT_NONE; p.c = C; p.ldc = ldc; p.n_valid = L.N;
   p.table = table; p.T = T;
   if (L.BN == 256) return launch_gemm<256, OUT_F32>(h, p, L.n_tiles, st);
   return arx_fail(h, ARX_ERR_INVALID, "tc_linear_f32: unsupported BN %d", L.BN);

@@ -99,6 +99,8 @@ struct arx_handle {
   float *dr_w = nullptr, *dr_b = nullptr, *d1_w = nullptr, *d1_b = nullptr;
   float *d2_w = nullptr, *d2_b = nullptr, *d3_w = nullptr, *d3_b = nullptr;
   ArxTcLinear tl_fc1, tl_fc2, tl_d1, tl_d2;
+  ArxTcLinear tl_heads;        // MetrABS heads Linear(1280 -> 288) in front of the heatmap decoder (arx_heads_*)
+  bool heads_loaded = false;
   bool tc_linears = false;     // frame MLP / projection / discriminator MLP run on tensor cores
   // support set
   int way = 0;
@@ -236,7 +238,7 @@ int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M,
 int arx_tc_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,
                       cudaStream_t st);
 int arx_tc_linear_f32(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *C, int ldc, const float *table, int T,
-                      cudaStream_t st);
+                      cudaStream_t st, bool with_bias = false);
 int arx_tc_linear_sigmoid_dot(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, const float *w3, const float *b3, float *out,
                               cudaStream_t st);
 
@@ -307,4 +309,5 @@ int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, 
 
 // ---- decode (arx_decode.cu) ------------------------------------------------------
 int arx_decode_launch(arx_handle *h, const float *logits, int64_t n_frames, const float *expand, int n_out,
-                      const float *K9, const float *R9, float *poses, uint8_t *valid, cudaStream_t st);
+                      const float *K9, const float *R9, float *poses, uint8_t *valid, cudaStream_t st, const float *Ks_dev = nullptr,
+                      const float *Rs_dev = nullptr);

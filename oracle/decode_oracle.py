@@ -148,3 +148,49 @@ def decode_frames(logits, expand_joints, indices, new_K, homo_inv, min_in_fov_fr
         poses[f] = p.reshape(-1)                                   # main.py:105
         valid[f] = True
     return poses, valid
+
+
+def rotation_mat_zaxis(angle):                                     # misc.py:299-307
+    sin, cos = np.sin(angle), np.cos(angle)
+    _0, _1 = np.zeros_like(angle), np.ones_like(angle)
+    return np.stack([np.stack([cos, -sin, _0], axis=-1), np.stack([sin, cos, _0], axis=-1), np.stack([_0, _0, _1], axis=-1)], axis=-2)
+
+
+def get_augmentations(num_aug, rot_aug_linspace_noend=True):      # misc.py:310-327
+    aug_gammas = np.linspace(0.6, 1.0, num_aug)
+    aug_angle_range = np.float32(np.deg2rad(25))
+    if rot_aug_linspace_noend:
+        aug_angles = np.linspace(-aug_angle_range, aug_angle_range, num_aug + 1)[:-1]
+    else:
+        aug_angles = np.linspace(-aug_angle_range, aug_angle_range, num_aug)
+    aug_scales = np.concatenate([np.linspace(0.8, 1.0, (num_aug + 1) // 2)[:-1], np.linspace(1.0, 1.1, num_aug - num_aug // 2)], axis=0)
+    aug_should_flip = (np.arange(num_aug) - num_aug // 2) % 2 != 0
+    aug_flipmat = np.array([[-1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float32)
+    aug_maybe_flipmat = np.where(aug_should_flip[:, np.newaxis, np.newaxis], aug_flipmat, np.eye(3))
+    return aug_should_flip, aug_maybe_flipmat @ rotation_mat_zaxis(-aug_angles), aug_gammas, aug_scales
+
+
+def tta_cameras(new_K, homo_inv, num_aug):
+    """hpe.py:88-93: per-augmentation intrinsics (scaled) and homographies (rotation/flip applied first)."""
+    flip, rotflip, _, scales = get_augmentations(num_aug)
+    K = np.tile(np.asarray(new_K).reshape(3, 3), (num_aug, 1, 1)).astype(np.float64)
+    for k in range(num_aug):
+        K[k, :2, :2] *= scales[k]
+    R = rotflip @ np.tile(np.asarray(homo_inv).reshape(3, 3), (num_aug, 1, 1))
+    return K, R, flip
+
+
+def decode_frames_cams(logits, expand_joints, indices, new_Ks, homo_invs, min_in_fov_frac=0.25):
+    """decode_frames with a camera per frame (the call the reference's decode makes for crop k taken as the only crop)."""
+    B = logits.shape[0]
+    poses = np.zeros((B, len(indices) * 3), np.float64)
+    valid = np.zeros((B,), bool)
+    for f in range(B):
+        p, v = decode_frames(logits[f:f + 1], expand_joints, indices, new_Ks[f], homo_invs[f], min_in_fov_frac)
+        poses[f], valid[f] = p[0], v[0]
+    return poses, valid
+
+
+def heads_forward(feats, weight, bias):
+    """modules/hpe/setup/4_create_heads_onnx.py:7-16: Linear(1280 -> 288) on (B,8,8,1280)."""
+    return feats @ np.asarray(weight).T + np.asarray(bias)

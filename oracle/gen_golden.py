@@ -174,6 +174,48 @@ def decode_case(name):
     print(name, poses_ref.shape, "valid", valid.mean())
 
 
+def tta_case(name):
+    """Pin the test-time-augmentation helpers against modules/hpe/utils/misc.py (get_augmentations, rotation_mat_zaxis) and
+    freeze a per-crop decode: crop k is decoded by the reference's own reconstruct_absolute with crop k's camera."""
+    sys.path.insert(0, REF)
+    import pickle
+    from modules.hpe.utils import misc as M
+    from oracle import decode_oracle as D
+    from oracle.synth import make_heatmaps
+    n = 5
+    ref = M.get_augmentations(n)
+    got = D.get_augmentations(n)
+    for a, b in zip(ref, got):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    K = D.realsense_K()
+    nk, R0 = M.homography(100, 300, 50, 450, K, 256)
+    # hpe.py:88-93 transcribed on the reference's own outputs
+    new_K = np.tile(nk, (n, 1, 1))
+    for k in range(n):
+        new_K[k, :2, :2] *= ref[3][k]
+    homo_inv = ref[1] @ np.tile(R0[0], (n, 1, 1))
+    Ks, Rs, flip = D.tta_cameras(nk, R0, n)
+    assert np.allclose(Ks, new_K, rtol=0, atol=0) and np.allclose(Rs, homo_inv, rtol=0, atol=0)
+    hm = make_heatmaps(n, seed=4)
+    p2, p3 = D.soft_argmax(hm)
+    E = np.load(os.path.join(REF, "assets/32_to_122.npy"))
+    st = pickle.load(open(os.path.join(REF, "assets/skeleton_types.pkl"), "rb"))
+    idx = np.array([int(i) for i in st["smpl+head_30"]["indices"]])
+    poses_ref = []
+    for f in range(n):
+        fov = M.is_within_fov(p2[f:f + 1])
+        a = M.reconstruct_absolute(p2[f:f + 1], p3[f:f + 1], new_K[f][None, ...], fov, weak_perspective=False)
+        p = a @ homo_inv[f]
+        p = (p.swapaxes(1, 2) @ E).swapaxes(1, 2)[:, idx][0]
+        poses_ref.append((p - p[0, :]).reshape(-1))
+    poses_ref = np.stack(poses_ref)
+    poses, valid = D.decode_frames_cams(hm, E, idx, Ks, Rs)
+    assert valid.all() and np.allclose(poses, poses_ref, rtol=1e-12, atol=1e-13)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), poses=poses_ref, new_K=new_K, homo_inv=homo_inv, flip=ref[0], rotflip=ref[1],
+                        gammas=ref[2], scales=ref[3], base_K=nk, base_R=R0)
+    print(name, poses_ref.shape)
+
+
 def support_set_fixture():
     """The reference's own saved support set (assets/saved/support_set.pkl + requires_focus.pkl, written by
     main.py:321-326 `save`): copied byte for byte as the interchange fixture (a data asset, not source).  It is an
@@ -188,6 +230,7 @@ def support_set_fixture():
 def main():
     os.makedirs(OUT, exist_ok=True)
     support_set_fixture()
+    tta_case("tta_5")
     from oracle.synth import Cfg
     trx_case("cfg1_w5_t16_structured", Cfg(), 64, 0, 1, "structured")
     trx_case("cfg1_w5_t16_iid", Cfg(), 64, 0, 3, "iid")

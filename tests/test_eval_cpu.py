@@ -84,3 +84,21 @@ def test_reference_support_set_fixture_through_oracle(golden_dir):
     for f in ss["lift"]["poses"].numpy():
         res, os_, rf = oa.inference({"sk": f})
     assert max(res, key=res.get) == "lift" and rf == {"hello": True, "get": True, "lift": False}
+
+
+def test_tta_helpers_match_reference_golden(golden_dir):
+    """get_augmentations / tta_cameras (misc.py:310-327, hpe.py:88-93): product host code and oracle against arrays frozen from
+    the reference's own functions."""
+    from isbfsar_b200 import decode as P
+    from oracle import decode_oracle as D
+    g = np.load(os.path.join(golden_dir, "tta_5.npz"))
+    for mod in (P, D):
+        flip, rotflip, gammas, scales = mod.get_augmentations(5)
+        assert np.array_equal(flip, g["flip"]) and np.array_equal(rotflip, g["rotflip"])
+        assert np.array_equal(gammas, g["gammas"]) and np.array_equal(scales, g["scales"])
+        K, R, f2 = mod.tta_cameras(g["base_K"], g["base_R"], 5)
+        assert np.array_equal(K, g["new_K"]) and np.array_equal(R, g["homo_inv"]) and np.array_equal(f2, g["flip"])
+    from oracle.synth import make_heatmaps
+    d64 = np.load(os.path.join(golden_dir, "decode_64.npz"))
+    poses, valid = D.decode_frames_cams(make_heatmaps(5, seed=4), d64["expand30"], np.arange(30), g["new_K"], g["homo_inv"])
+    assert valid.all() and np.allclose(poses, g["poses"], rtol=1e-12, atol=1e-13)

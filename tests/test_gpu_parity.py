@@ -840,3 +840,51 @@ def test_second_device_in_same_process():
         m2.set_support(poses=torch.from_numpy(support[0]).to("cuda:1"))
         c, d = m2.score(torch.from_numpy(query).to("cuda:1"))
     assert torch.equal(a.cpu(), c.cpu()) and torch.equal(b.cpu(), d.cpu())
+
+
+def test_tta_decode_per_crop_cameras(golden_dir):
+    """Test-time augmentation (hpe.py:87-93, misc.py:310-327): five crops, each decoded with its own scaled intrinsics and its own
+    rotation/flip, in one launch; per-crop poses against the reference's decode of that crop."""
+    from isbfsar_b200 import HeatmapDecoder
+    g = np.load(os.path.join(golden_dir, "tta_5.npz"))
+    d64 = np.load(os.path.join(golden_dir, "decode_64.npz"))
+    m, _ = make_model(Cfg(), 0)
+    dec = HeatmapDecoder(m, d64["expand30"], None, g["base_K"], g["base_R"])
+    hm = torch.from_numpy(make_heatmaps(5, seed=4)).cuda()
+    poses, valid, mean = dec.decode_tta(hm)
+    assert valid.all()
+    ref = g["poses"]
+    assert np.abs(poses.cpu().numpy() - ref).max() < 1e-4 * np.abs(ref).max()
+    assert np.abs(mean.cpu().numpy() - ref.mean(0)).max() < 1e-4 * np.abs(ref).max()
+    assert (poses[:, :3] == 0).all()
+    # one camera for all frames == the per-frame entry point with that camera repeated
+    p1, v1 = dec.decode(hm)
+    p2, v2 = dec.decode_cams(hm, np.tile(g["base_K"], (5, 1, 1)), np.tile(g["base_R"].reshape(3, 3), (5, 1, 1)))
+    assert torch.equal(p1, p2) and torch.equal(v1, v2)
+
+
+def test_metrabs_heads_gemm_feeds_the_decoder(golden_dir):
+    """Linear(1280 -> 288) over the (8,8,1280) feature map (4_create_heads_onnx.py:7-16) on tensor cores, fp16 operands like the
+    reference's TensorRT-fp16 engine: logits within 2e-3 of the fp32 product, decoded poses within 1e-3 of the pose scale."""
+    from isbfsar_b200 import HeatmapDecoder
+    from isbfsar_b200.decode import MetrabsHeads
+    from oracle import decode_oracle as D
+    d64 = np.load(os.path.join(golden_dir, "decode_64.npz"))
+    rng = np.random.default_rng(11)
+    B = 70                                                       # 4480 rows: ragged last 128-row tile
+    target = make_heatmaps(B, seed=6).reshape(B * 64, 288)
+    # features whose exact heads output is a heatmap with planted peaks: feats = target @ pinv(W) (+ null-space noise)
+    W = (rng.standard_normal((288, 1280)) / np.sqrt(1280)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(288)).astype(np.float32)
+    feats = ((target - b) @ np.linalg.pinv(W).T).astype(np.float32).reshape(B, 8, 8, 1280)
+    m, _ = make_model(Cfg(), 0)
+    heads = MetrabsHeads(m, W, b)
+    logits = heads(torch.from_numpy(feats).cuda())
+    ref = D.heads_forward(feats.astype(np.float64), W.astype(np.float64), b.astype(np.float64))
+    assert logits.shape == (B, 8, 8, 288)
+    assert np.abs(logits.cpu().numpy() - ref).max() < 2e-3 * np.abs(ref).max()
+    dec = HeatmapDecoder(m, d64["expand30"], None, d64["new_K"], d64["homo_inv"])
+    poses, valid = dec.decode(logits)
+    rp, rv = D.decode_frames(ref.astype(np.float32), d64["expand30"], np.arange(30), d64["new_K"], d64["homo_inv"])
+    assert np.array_equal(valid.cpu().numpy(), rv) and rv.all()
+    assert np.abs(poses.cpu().numpy() - rp).max() < 1e-3 * np.abs(rp).max()
