@@ -738,14 +738,31 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_check = float((outs[(e2e_steps - 1) % 3][0] - ref_logits.cpu()).abs().max())
+    # the same with fp16 host rows (arx_score_host_submit_f16): half the H2D bytes, for producers that emit fp16
+    q_pin16 = torch.from_numpy(query).to(torch.float16).pin_memory()
+    for k in range(2):
+        model.score_host_async(q_pin16, out=outs[k]).result()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    pending = []
+    for k in range(e2e_steps):
+        pending.append(model.score_host_async(q_pin16, out=outs[k % 3]))
+        if len(pending) == 2:
+            pending.pop(0).result()
+    for tk in pending:
+        tk.result()
+    torch.cuda.synchronize()
+    e2e16_s = time.perf_counter() - t0
 
-    t = torch.tensor([total_ms, e2e_s, float(launches), e2e_sync_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s, float(launches), e2e_sync_s, e2e16_s], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        total_ms, e2e_s, launches, e2e_sync_s = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3])
+        total_ms, e2e_s, launches, e2e_sync_s, e2e16_s = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3]), float(tmax[4])
     value = world * B * n_steps_total / (total_ms * 1e-3)
     e2e_val = world * B * e2e_steps / e2e_s
 
@@ -821,6 +838,8 @@ def main():
                         "mode": "streaming: arx_score_host_submit/_wait, two requests in flight, pinned host buffers",
                         "blocking_value": world * B * e2e_steps / e2e_sync_s,
                         "blocking_mode": "one synchronous arx_score_host call at a time",
+                        "f16_rows_value": world * B * e2e_steps / e2e16_s, "f16_rows_h2d_bytes_per_step": world * B * T * J3 * 2,
+                        "f16_rows_mode": "streaming, host rows already fp16 (arx_score_host_submit_f16): bit-identical scores for fp16-representable inputs",
                         "max_abs_diff_vs_device_path": e2e_check,
                         "timing": "host wall clock from first submit to last result, max over ranks"},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_per_kernel": per_kernel, "sustained": sustained,

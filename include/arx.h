@@ -150,6 +150,12 @@ ARX_API int arx_debug_attention(arx_handle *h, const float *query_dev, int64_t n
 ARX_API int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows,
                    float *logits_host, float *is_true_host, int32_t *chosen_host);
 
+/* fp16 HOST rows (IEEE binary16, same (B,T,3J) layout): half the PCIe bytes of the fp32 entry points.  The first GEMM's
+ * operand image is fp16 in any case, so for inputs representable in fp16 the results are bit-identical to the fp32 entry
+ * points.  Available where the linear layers run on tensor cores (all BASELINE configs); ARX_ERR_INVALID otherwise. */
+ARX_API int arx_score_host_f16(arx_handle *h, const uint16_t *query_host_f16, int64_t n_windows,
+                       float *logits_host, float *is_true_host, int32_t *chosen_host);
+
 /* Streaming variant of arx_score_host: returns as soon as the copies and kernels are enqueued on the handle's
  * internal copy/compute streams; up to ARX_HOST_DEPTH requests may be in flight, so the H2D copy of request i+1
  * overlaps the scoring of request i.  arx_score_host_wait blocks until request `ticket` (returned by submit)
@@ -157,6 +163,8 @@ ARX_API int arx_score_host(arx_handle *h, const float *query_host, int64_t n_win
 #define ARX_HOST_DEPTH 2
 ARX_API int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_windows,
                           float *logits_host, float *is_true_host, int32_t *chosen_host, int64_t *ticket);
+ARX_API int arx_score_host_submit_f16(arx_handle *h, const uint16_t *query_host_f16, int64_t n_windows,
+                              float *logits_host, float *is_true_host, int32_t *chosen_host, int64_t *ticket);
 ARX_API int arx_score_host_wait(arx_handle *h, int64_t ticket);
 
 /* Resident streaming scorer: ActionRecognizer.inference (modules/ar/ar.py:30-84, called once per camera frame from

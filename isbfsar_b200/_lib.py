@@ -15,7 +15,7 @@ EXPORTS = [
     "arx_tuple_table", "arx_embed", "arx_set_support_poses", "arx_set_support_features",
     "arx_get_support_features", "arx_support_way", "arx_support_blob_bytes", "arx_export_support",
     "arx_import_support", "arx_score", "arx_score_features", "arx_debug_attention", "arx_score_host",
-    "arx_score_episodes", "arx_stream_push", "arx_stream_reset", "arx_score_host_submit", "arx_score_host_wait", "arx_decode_heatmaps", "arx_decode_heatmaps_cams", "arx_heads_load", "arx_heads_forward", "arx_launch_count", "arx_last_path", "arx_profile_enable", "arx_profile_read", "arx_debug_set", "arx_debug_read_trace",
+    "arx_score_episodes", "arx_stream_push", "arx_stream_reset", "arx_score_host_submit", "arx_score_host_wait", "arx_score_host_f16", "arx_score_host_submit_f16", "arx_decode_heatmaps", "arx_decode_heatmaps_cams", "arx_heads_load", "arx_heads_forward", "arx_launch_count", "arx_last_path", "arx_profile_enable", "arx_profile_read", "arx_debug_set", "arx_debug_read_trace",
 ]
 
 
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
         "arx_stream_reset": (C.c_int, [H]),
         "arx_score_host_submit": (C.c_int, [H, VP, I64, VP, VP, VP, C.POINTER(I64)]),
         "arx_score_host_wait": (C.c_int, [H, I64]),
+        "arx_score_host_f16": (C.c_int, [H, VP, I64, VP, VP, VP]),
+        "arx_score_host_submit_f16": (C.c_int, [H, VP, I64, VP, VP, VP, C.POINTER(I64)]),
         "arx_decode_heatmaps": (C.c_int, [H, VP, I64, VP, I32, VP, VP, VP, VP, VP]),
         "arx_decode_heatmaps_cams": (C.c_int, [H, VP, I64, VP, I32, VP, VP, VP, VP, VP]),
         "arx_heads_load": (C.c_int, [H, VP, VP, I32, VP]),

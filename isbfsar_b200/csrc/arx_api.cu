@@ -893,7 +893,7 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
   if (capturable && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf) {
     ArxScoreGraphKey key;
     key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
-    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0);
+    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0) | (h->query_f16 ? (1 << 22) : 0);
     key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
     sg = score_graph_lookup(h, key);
   }
@@ -1092,14 +1092,24 @@ int arx_debug_attention(arx_handle *h, const float *query_dev, int64_t n_windows
   return rc;
 }
 
-int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, float *logits_host, float *is_true_host,
-                   int32_t *chosen_host) {
-  if (!h || !query_host || !logits_host || n_windows < 0) return arx_fail(h, ARX_ERR_INVALID, "score_host: bad argument");
+// fp16 host rows go straight into the fp16 operand image of the first GEMM (the fp32 path rounds to fp16 there anyway, so
+// results are bit-identical for inputs that are representable in fp16); only the T=16 pair pipeline and the tiled kernels
+// with tensor-core linear layers read halves
+static bool f16_input_ok(const arx_handle *h) {
+  const ArxTransformer &tr = h->tr[0];
+  return h->tc_linears && (h->tc_variant & 4) == 0 && ((route_gen3(h, tr) && tr.ks_img) || route_tiled(h, tr));
+}
+
+static int score_host_impl(arx_handle *h, const void *query_host_v, bool f16, int64_t n_windows, float *logits_host, float *is_true_host,
+                           int32_t *chosen_host) {
+  if (!h || !query_host_v || !logits_host || n_windows < 0) return arx_fail(h, ARX_ERR_INVALID, "score_host: bad argument");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score_host: support set not set");
   if (n_windows == 0) return ARX_OK;
+  if (f16 && !f16_input_ok(h)) return arx_fail(h, ARX_ERR_INVALID, "score_host_f16: fp16 rows need the tensor-core linear layers (this shape scores on the fp32 kernels)");
+  const char *query_host = static_cast<const char *>(query_host_v);
   const bool disc = h->cfg.has_discriminator && is_true_host;
   const int way = h->way;
-  const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);
+  const size_t in_per = (size_t)h->T * h->J3 * (f16 ? sizeof(__half) : sizeof(float));
   const size_t out_per = (size_t)(way + 2) * sizeof(float);   // logits | is_true | chosen
   // copy/compute overlap needs at least two chunks per call, but small chunks waste the GPU (fixed per-launch costs):
   // halve the batch (rounded to whole 128-row tiles), never below 1024 windows
@@ -1132,9 +1142,11 @@ int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, fl
     float *dlog = static_cast<float *>(h->dev_out[s]);
     float *dist = dlog + (size_t)stage * way;
     int32_t *dch = reinterpret_cast<int32_t *>(dist + stage);
-    ARX_CUDA(h, cudaMemcpyAsync(din, query_host + b0 * h->T * h->J3, n * in_per, cudaMemcpyHostToDevice, st));
+    ARX_CUDA(h, cudaMemcpyAsync(din, query_host + b0 * in_per, n * in_per, cudaMemcpyHostToDevice, st));
     if (i > 0) ARX_CUDA(h, cudaStreamWaitEvent(st, h->stage_ev[s ^ 1], 0));   // previous chunk done with the workspace
+    h->query_f16 = f16;
     int rc = score_impl(h, 0, din, nullptr, n, dlog, disc ? dist : nullptr, dch, nullptr, nullptr, st);
+    h->query_f16 = false;
     if (rc) return rc;
     ARX_CUDA(h, cudaEventRecord(h->stage_ev[s], st));
     ARX_CUDA(h, cudaMemcpyAsync(logits_host + b0 * way, dlog, (size_t)n * way * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1146,13 +1158,23 @@ int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, fl
   return ARX_OK;
 }
 
-int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_windows, float *logits_host, float *is_true_host,
-                          int32_t *chosen_host, int64_t *ticket) {
+int arx_score_host(arx_handle *h, const float *query_host, int64_t n_windows, float *logits_host, float *is_true_host, int32_t *chosen_host) {
+  return score_host_impl(h, query_host, false, n_windows, logits_host, is_true_host, chosen_host);
+}
+int arx_score_host_f16(arx_handle *h, const uint16_t *query_host_f16, int64_t n_windows, float *logits_host, float *is_true_host,
+                       int32_t *chosen_host) {
+  return score_host_impl(h, query_host_f16, true, n_windows, logits_host, is_true_host, chosen_host);
+}
+
+static int score_host_submit_impl(arx_handle *h, const void *query_host, bool f16, int64_t n_windows, float *logits_host, float *is_true_host,
+                                  int32_t *chosen_host, int64_t *ticket) {
   if (!h || !query_host || !logits_host || !ticket || n_windows <= 0) return arx_fail(h, ARX_ERR_INVALID, "score_host_submit: bad argument");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score_host_submit: support set not set");
+  if (f16 && !f16_input_ok(h)) return arx_fail(h, ARX_ERR_INVALID, "score_host_submit_f16: fp16 rows need the tensor-core linear layers");
   const bool disc = h->cfg.has_discriminator && is_true_host;
   const int way = h->way;
-  const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);
+  const size_t in_per = (size_t)h->T * h->J3 * sizeof(float);          // staging is sized for fp32 rows (fp16 requests use half of it)
+  const size_t in_bytes = (size_t)n_windows * h->T * h->J3 * (f16 ? sizeof(__half) : sizeof(float));
   const size_t out_per = (size_t)(way + 2) * sizeof(float);
   if (!h->hs_h2d) {
     ARX_CUDA(h, cudaStreamCreateWithFlags(&h->hs_h2d, cudaStreamNonBlocking));
@@ -1185,12 +1207,14 @@ int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_wind
   // H2D of request id may start once the request that used this slot (id - DEPTH) has been scored
   const bool slot_used = id - h->hs_base >= ARX_HOST_DEPTH;     // this slot's buffers carried an earlier request since the last reallocation
   if (slot_used) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_h2d, h->hs_ev_comp[s], 0));
-  ARX_CUDA(h, cudaMemcpyAsync(din, query_host, n_windows * in_per, cudaMemcpyHostToDevice, h->hs_h2d));
+  ARX_CUDA(h, cudaMemcpyAsync(din, query_host, in_bytes, cudaMemcpyHostToDevice, h->hs_h2d));
   ARX_CUDA(h, cudaEventRecord(h->hs_ev_h2d[s], h->hs_h2d));
   // scoring: after its inputs arrived and after the results previously held in this slot went back to the host
   ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_h2d[s], 0));
   if (slot_used) ARX_CUDA(h, cudaStreamWaitEvent(h->hs_comp, h->hs_ev_done[s], 0));
+  h->query_f16 = f16;
   int rc = score_impl(h, 0, din, nullptr, n_windows, dlog, disc ? dist : nullptr, dch, nullptr, nullptr, h->hs_comp);
+  h->query_f16 = false;
   if (rc) return rc;
   ARX_CUDA(h, cudaEventRecord(h->hs_ev_comp[s], h->hs_comp));
   ARX_CUDA(h, cudaStreamWaitEvent(h->hs_d2h, h->hs_ev_comp[s], 0));
@@ -1201,6 +1225,15 @@ int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_wind
   *ticket = id;
   h->hs_submitted = id + 1;
   return ARX_OK;
+}
+
+int arx_score_host_submit(arx_handle *h, const float *query_host, int64_t n_windows, float *logits_host, float *is_true_host,
+                          int32_t *chosen_host, int64_t *ticket) {
+  return score_host_submit_impl(h, query_host, false, n_windows, logits_host, is_true_host, chosen_host, ticket);
+}
+int arx_score_host_submit_f16(arx_handle *h, const uint16_t *query_host_f16, int64_t n_windows, float *logits_host, float *is_true_host,
+                              int32_t *chosen_host, int64_t *ticket) {
+  return score_host_submit_impl(h, query_host_f16, true, n_windows, logits_host, is_true_host, chosen_host, ticket);
 }
 
 int arx_score_host_wait(arx_handle *h, int64_t ticket) {

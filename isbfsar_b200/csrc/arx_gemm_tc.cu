@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) k_gemm_tc(const GemmParams p) {
   if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, TM_COLS); }
 }
 
-// fp32 row-major [M][lda] (K valid columns) -> fp16 activation image [ceil(M/128)][nk][128 x 64]; zero padded.
-__global__ void __launch_bounds__(256) k_rows_to_img(const float *__restrict__ X, int lda, int K, int64_t M, __half *__restrict__ img, int nk,
+// fp32 (or fp16) row-major [M][lda] (K valid columns) -> fp16 activation image [ceil(M/128)][nk][128 x 64]; zero padded.
+template <class TIn>
+__global__ void __launch_bounds__(256) k_rows_to_img(const TIn *__restrict__ X, int lda, int K, int64_t M, __half *__restrict__ img, int nk,
                                                      int onehot_sub) {
   pdl_trigger();
   pdl_wait();
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) k_rows_to_img(const float *__restrict__ X
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int k = ch * 8 + i;
-    x[i] = (row < M && k < K) ? __ldg(X + row * (int64_t)lda + k) : 0.f;
+    x[i] = (row < M && k < K) ? (float)X[row * (int64_t)lda + k] : 0.f;
     if (onehot_sub >= 0 && (ch >> 3) == onehot_sub) {          // one-hot(row % 16) at columns t and 16 + t of this sub-tile
       const int c = (ch & 7) * 8 + i;
       x[i] = (c < 32 && (c & 15) == (int)(row & 15)) ? 1.f : 0.f;
@@ -287,7 +288,12 @@ int arx_tc_linear_prepare(arx_handle *h, ArxTcLinear &L, const float *W, int ldw
 
 int arx_tc_rows_to_img(arx_handle *h, const float *X, int lda, int K, int64_t M, __half *img, int nk, int onehot_sub, cudaStream_t st) {
   const int64_t total = ((M + 127) / 128) * 128 * nk * 8;
-  ARX_CUDA(h, arx_launch_pdl(k_rows_to_img, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, h->pdl, X, lda, K, M, img, nk, onehot_sub));
+  if (h->query_f16) {          // the caller's rows are fp16 (arx_score_host*_f16): same image, no rounding step
+    k_rows_to_img<__half><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half *>(X), lda, K, M, img, nk, onehot_sub);
+    ARX_LAUNCH_CHECK(h);
+    return ARX_OK;
+  }
+  ARX_CUDA(h, arx_launch_pdl(k_rows_to_img<float>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, h->pdl, X, lda, K, M, img, nk, onehot_sub));
   h->launches++;
   return ARX_OK;
 }

@@ -148,6 +148,7 @@ struct arx_handle {
   double prof_ms[ARX_N_STAGES] = {0, 0, 0, 0, 0};
   int64_t prof_chunks = 0;
   int last_path = 0;
+  bool query_f16 = false;       // set around a scoring pass whose query rows are fp16 (arx_score_host*_f16): first-stage image kernel reads halves
   std::vector<ArxScoreGraph> graphs;     // small LRU cache (arx_score with recurring arguments)
   uint64_t graph_tick = 0, support_gen = 0, weights_gen = 0;
   uint64_t support_seq = 0;              // increments whenever a new support set is set / imported

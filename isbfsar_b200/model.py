@@ -345,14 +345,14 @@ class TRXOS(nn.Module):
         h = self._ensure()
         lib = _lib.load()
         q = query_cpu
-        assert q.device.type == "cpu" and q.dtype == torch.float32 and q.is_contiguous()
+        assert q.device.type == "cpu" and q.dtype in (torch.float32, torch.float16) and q.is_contiguous()
         B = q.shape[0]
         way = lib.arx_support_way(h)
         logits, is_true = self._host_out(B, way, out)
+        fn = lib.arx_score_host if q.dtype == torch.float32 else lib.arx_score_host_f16      # fp16 rows: half the PCIe bytes
         with torch.cuda.device(self._device()):
-            _lib.check(lib.arx_score_host(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
-                                          C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None),
-                       h, "arx_score_host")
+            _lib.check(fn(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
+                          C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None), h, "arx_score_host")
         return logits, is_true
 
     def score_host_async(self, query_cpu, out=None):
@@ -362,15 +362,15 @@ class TRXOS(nn.Module):
         h = self._ensure()
         lib = _lib.load()
         q = query_cpu
-        assert q.device.type == "cpu" and q.dtype == torch.float32 and q.is_contiguous()
+        assert q.device.type == "cpu" and q.dtype in (torch.float32, torch.float16) and q.is_contiguous()
         B = q.shape[0]
         way = lib.arx_support_way(h)
         logits, is_true = self._host_out(B, way, out)
         t = C.c_int64()
+        fn = lib.arx_score_host_submit if q.dtype == torch.float32 else lib.arx_score_host_submit_f16
         with torch.cuda.device(self._device()):
-            _lib.check(lib.arx_score_host_submit(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
-                                                 C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None,
-                                                 C.byref(t)), h, "arx_score_host_submit")
+            _lib.check(fn(h, C.c_void_p(q.data_ptr()), B, C.c_void_p(logits.data_ptr()),
+                          C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None, C.byref(t)), h, "arx_score_host_submit")
         return _HostTicket(self, int(t.value), q, logits, is_true)
 
     def score_episodes(self, query, poses=None, features=None):

@@ -888,3 +888,25 @@ def test_metrabs_heads_gemm_feeds_the_decoder(golden_dir):
     rp, rv = D.decode_frames(ref.astype(np.float32), d64["expand30"], np.arange(30), d64["new_K"], d64["homo_inv"])
     assert np.array_equal(valid.cpu().numpy(), rv) and rv.all()
     assert np.abs(poses.cpu().numpy() - rp).max() < 1e-3 * np.abs(rp).max()
+
+
+def test_fp16_host_rows_are_bit_identical():
+    """arx_score_host*_f16: fp16 host rows (half the PCIe bytes) give the same bits as fp32 rows holding the same values, on the
+    T=16 pair pipeline and on the tiled kernels; shapes on the fp32 kernels refuse loudly."""
+    for cfg, B, path in [(Cfg(), 600, 2), (Cfg(way=20, seq_len=32, temp_set=[2, 3]), 40, 3)]:
+        m, sd = make_model(cfg, 0)
+        support, labels, query, _ = make_episode(cfg, B, 141, "structured")
+        q16 = torch.from_numpy(query).to(torch.float16)
+        q32 = q16.to(torch.float32)                               # the same values, representable in fp16
+        m.set_support(poses=torch.from_numpy(support[0]).cuda())
+        a = m.score_host(q32.pin_memory())
+        b = m.score_host(q16.pin_memory())
+        c = m.score_host_async(q16.pin_memory()).result()
+        assert m.last_path() == path
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+        lo, it = TrxOracle(cfg, sd).score(support, labels, query[:32], chunk=16)
+        assert rel_err(b[0][:32], lo).max() < TOL_TC and rel_err(b[1][:32], it).max() < TOL_TC
+    m, _ = make_model(Cfg(), 0, force_path=1)
+    m.set_support(poses=torch.from_numpy(support[0][:5, :16]).cuda())
+    with pytest.raises(ValueError):
+        m.score_host(torch.zeros((4, 16, 90), dtype=torch.float16).pin_memory())
