@@ -322,15 +322,20 @@ def other_configs(torch, dev, peaks):
 
         def e2e():
             p, _ = dec.decode(hm)
-            w = p.unfold(0, 16, 1).permute(0, 2, 1).contiguous()         # 1009 sliding windows
-            return m.score(w)
+            return m.score_frames(p)                                     # 1009 sliding windows formed on the device
         ms = timed_ms(torch, e2e, 10)
+
+        def e2e_windows():
+            p, _ = dec.decode(hm)
+            return m.score(p.unfold(0, 16, 1).permute(0, 2, 1).contiguous())
+        ms_w = timed_ms(torch, e2e_windows, 10)
         by = 4 * nfr * (73728 + 360)
         return {"decode_kernel": {"workload": "4096 frames (8,8,288) fp32 -> 30-joint poses", "ms": ms_dec, "frames_per_s": 4 * nfr / ms_dec * 1e3,
                                   "achieved_gbs": by / ms_dec / 1e6, "frac_of_hbm": by / ms_dec / 1e6 / peaks["hbm_gbs"], "bound": "hbm",
                                   "algorithmic_bytes_per_frame": 73728 + 360},
-                "end_to_end": {"workload": "1024 heatmap frames -> decode -> 1009 sliding windows -> 5-way scoring", "ms": ms,
-                               "frames_per_s": nfr / ms * 1e3, "valid_frames": int(valid.sum())}}
+                "end_to_end": {"workload": "1024 heatmap frames -> decode -> 1009 sliding windows (frame-stream form: every frame embedded "
+                                           "once, windows formed on the device) -> 5-way scoring", "ms": ms, "frames_per_s": nfr / ms * 1e3,
+                               "valid_frames": int(valid.sum()), "ms_with_explicit_windows": ms_w}}
 
     def stream():
         from isbfsar_b200 import ActionRecognizer

@@ -122,6 +122,14 @@ ARX_API int arx_import_support(arx_handle *h, const void *blob_dev, int32_t way,
 ARX_API int arx_score(arx_handle *h, const float *query_dev, int64_t n_windows,
               float *logits_dev, float *is_true_dev, int32_t *chosen_dev, void *stream);
 
+/* Frame-stream form of arx_score: frames_dev (n_frames, 3J) is a sequence of camera frames and EVERY sliding window of
+ * seq_len consecutive frames is scored (window w = frames w .. w+T-1, what n_frames successive ActionRecognizer.inference
+ * calls see, ar.py:42-50): logits_dev (n_frames-T+1, W), is_true_dev (n_frames-T+1).  Each frame is embedded and projected
+ * ONCE (the projection is position-independent; the positional table is added per window position when the windows are
+ * formed on the device), and a caller uploads 3J floats per window instead of T*3J. */
+ARX_API int arx_score_frames(arx_handle *h, const float *frames_dev, int64_t n_frames,
+                     float *logits_dev, float *is_true_dev, int32_t *chosen_dev, void *stream);
+
 /* TRXOS.forward in the training / evaluation call shape (modules/ar/utils/train.py:110-120,
  * modules/ar/utils/test/compute_fsos.py:89-98): every batch row is its own EPISODE -- query i is scored against
  * ITS OWN `way` support classes (model.py:59-148 never mixes batch rows).  All episodes go through the batched

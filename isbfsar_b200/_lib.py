@@ -15,7 +15,7 @@ EXPORTS = [
     "arx_tuple_table", "arx_embed", "arx_set_support_poses", "arx_set_support_features",
     "arx_get_support_features", "arx_support_way", "arx_support_blob_bytes", "arx_export_support",
     "arx_import_support", "arx_score", "arx_score_features", "arx_debug_attention", "arx_score_host",
-    "arx_score_episodes", "arx_stream_push", "arx_stream_reset", "arx_score_host_submit", "arx_score_host_wait", "arx_score_host_f16", "arx_score_host_submit_f16", "arx_decode_heatmaps", "arx_decode_heatmaps_cams", "arx_heads_load", "arx_heads_forward", "arx_launch_count", "arx_last_path", "arx_profile_enable", "arx_profile_read", "arx_debug_set", "arx_debug_read_trace",
+    "arx_score_episodes", "arx_score_frames", "arx_stream_push", "arx_stream_reset", "arx_score_host_submit", "arx_score_host_wait", "arx_score_host_f16", "arx_score_host_submit_f16", "arx_decode_heatmaps", "arx_decode_heatmaps_cams", "arx_heads_load", "arx_heads_forward", "arx_launch_count", "arx_last_path", "arx_profile_enable", "arx_profile_read", "arx_debug_set", "arx_debug_read_trace",
 ]
 
 
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
         "arx_import_support": (C.c_int, [H, VP, I32, VP]),
         "arx_score": (C.c_int, [H, VP, I64, VP, VP, VP, VP]),
         "arx_score_features": (C.c_int, [H, I32, VP, I64, VP, VP]),
+        "arx_score_frames": (C.c_int, [H, VP, I64, VP, VP, VP, VP]),
         "arx_score_episodes": (C.c_int, [H, VP, I32, I32, VP, I64, VP, VP, VP, VP]),
         "arx_debug_attention": (C.c_int, [H, VP, I64, VP, VP, VP]),
         "arx_score_host": (C.c_int, [H, VP, I64, VP, VP, VP]),

@@ -95,10 +95,11 @@ struct Fp32Ws {
   float *H1, *FE, *G, *Kq, *Vq, *Z, *partial, *y, *h1, *h2;
   __half *kq_img, *x_img, *h_img, *f_img, *y_img, *h1_img;
   float *uab;
+  float *P, *U;              // frame-stream form: per-frame position-independent projections / head columns
   size_t bytes;
 };
 Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, void *base,
-                  bool tc = false, bool tuples32 = true, bool tcl = false, bool tc_head = false) {
+                  bool tc = false, bool tuples32 = true, bool tcl = false, bool tc_head = false, bool stream = false) {
   Carver c(base);
   Fp32Ws w{};
   const int nb = tc ? 4 : (tr.N + 63) / 64;
@@ -121,6 +122,8 @@ Fp32Ws carve_fp32(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, b
   w.y = disc32 ? c.take<float>(n * tr.N * h->T) : nullptr;
   w.h1 = disc32 ? c.take<float>(n * 256) : nullptr;
   w.h2 = disc32 ? c.take<float>(n * 64) : nullptr;
+  w.P = stream ? c.take<float>((n + h->T) * 2 * tr.c * h->D) : nullptr;
+  w.U = stream ? c.take<float>((n + h->T) * 32) : nullptr;
   w.bytes = c.off + 256;
   return w;
 }
@@ -234,7 +237,7 @@ void arx_destroy(arx_handle *h) {
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
   for (ArxTcLinear *L : {&h->tl_fc1, &h->tl_fc2, &h->tl_d1, &h->tl_d2, &h->tl_heads}) { cudaFree(L->w_img); cudaFree(L->bias); }
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
-    cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); cudaFree(h->tr[i].tl_uab.w_img); cudaFree(h->tr[i].tl_uab.bias);
+    cudaFree(h->tr[i].tl_proj.w_img); cudaFree(h->tr[i].tl_proj.bias); cudaFree(h->tr[i].tl_proj_nt.w_img); cudaFree(h->tr[i].tl_proj_nt.bias); cudaFree(h->tr[i].tl_uab.w_img); cudaFree(h->tr[i].tl_uab.bias);
     cudaFree(h->tr[i].wc); cudaFree(h->tr[i].tcomp);
   }
   for (int i = 0; i < ARX_HOST_DEPTH; ++i) {
@@ -333,6 +336,7 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
         if (!tr.wp_ext) ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.wp_ext), (size_t)2 * tr.c * h->D * (h->F + 32) * sizeof(float)));
         if ((rc = arx_tc_build_wp_ext(h, tr.wp, tr.bp, tr.wp_ext, 2 * tr.c * h->D, h->F, st))) return rc;
         if ((rc = arx_tc_linear_prepare(h, tr.tl_proj, tr.wp_ext, h->F + 32, nullptr, 2 * tr.c * h->D, h->F + 32, 256, st))) return rc;
+        if ((rc = arx_tc_linear_prepare(h, tr.tl_proj_nt, tr.wp, h->F, nullptr, 2 * tr.c * h->D, h->F, 256, st))) return rc;
       } else if ((rc = arx_tc_linear_prepare(h, tr.tl_proj, tr.wp, h->F, nullptr, 2 * tr.c * h->D, h->F, 256, st))) return rc;
     }
     if (h->cfg.has_discriminator) {
@@ -758,10 +762,11 @@ template <class F> static int score_segment(arx_handle *h, ArxScoreGraph *g, int
 // ---- scoring on the tiled any-N tcgen05 kernels (arx_tcn.cu) -----------------------------------------------------
 struct TcnWs {
   __half *x_img, *h_img, *f_img, *kq, *y_img, *h1_img;
-  float *H1, *FE, *G, *partial, *uab, *y, *h1, *h2;
+  float *H1, *FE, *G, *partial, *uab, *y, *h1, *h2, *P;
   size_t bytes;
 };
-static TcnWs carve_tcn(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, bool tcl, void *base) {
+static TcnWs carve_tcn(arx_handle *h, const ArxTransformer &tr, int64_t n, int way, bool from_frames, bool disc, bool tcl, void *base,
+                       bool stream = false) {
   Carver c(base);
   TcnWs w{};
   const int64_t rows = n * h->T, rows_pad = (rows + 127) / 128 * 128, n_pad = (n + 127) / 128 * 128;
@@ -786,6 +791,7 @@ static TcnWs carve_tcn(arx_handle *h, const ArxTransformer &tr, int64_t n, int w
       w.h2 = c.take<float>(n * 64);
     }
   }
+  w.P = stream ? c.take<float>((n + h->T) * 2 * tr.c * h->D) : nullptr;
   w.bytes = c.off + 256;
   return w;
 }
@@ -818,20 +824,20 @@ static int tcn_backend(arx_handle *h, const ArxTransformer &tr, const TcnWs &w, 
 }
 
 static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
-                     float *is_true_dev, int32_t *chosen_dev, cudaStream_t st) {
+                     float *is_true_dev, int32_t *chosen_dev, cudaStream_t st, bool frames_stream = false) {
   const ArxTransformer &tr = h->tr[ti];
   const bool from_frames = query_dev != nullptr, disc = is_true_dev != nullptr, tcl = h->tc_linears && (h->tc_variant & 4) == 0;
   const int way = h->way;
   if (!tr.kc_tiles) return arx_fail(h, ARX_ERR_STATE, "score: support operands of the tiled kernels are missing (set the support set again)");
   if (disc && !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "score: the open-set head of the tiled kernels needs pair tuples and T <= 32");
   // windows per pass: workspace budget (the query tiles are 32 KB per 128 tuples per window)
-  const size_t per = carve_tcn(h, tr, 128, way, from_frames, disc, tcl, nullptr).bytes / 128 + 1;
+  const size_t per = carve_tcn(h, tr, 128, way, from_frames, disc, tcl, nullptr, frames_stream).bytes / 128 + 1;
   int64_t chunk = h->cfg.max_chunk > 0 ? h->cfg.max_chunk : 4096;
   chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(chunk, (int64_t)(((size_t)3 << 30) / per)), n_windows));
-  const size_t need = carve_tcn(h, tr, chunk, way, from_frames, disc, tcl, nullptr).bytes + (chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256);
+  const size_t need = carve_tcn(h, tr, chunk, way, from_frames, disc, tcl, nullptr, frames_stream).bytes + (chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256);
   int rc = arx_ws_reserve(h, need);
   if (rc) return rc;
-  TcnWs w = carve_tcn(h, tr, chunk, way, from_frames, disc, tcl, h->ws);
+  TcnWs w = carve_tcn(h, tr, chunk, way, from_frames, disc, tcl, h->ws, frames_stream);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + need - (size_t)chunk * sizeof(int32_t) - 256);
   const int ldg = 2 * tr.c * h->D;
   h->last_path = 3;
@@ -839,7 +845,24 @@ static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float 
     const int64_t n = std::min(chunk, n_windows - b0), rows = n * h->T;
     if ((rc = prof_mark(h, 0, st))) return rc;
     const float *FE = nullptr;
-    if (tcl) {
+    if (frames_stream) {
+      // frame stream: embed and project every frame once (position-independent), then form the windows' projections
+      const int64_t rows_f = n + h->T - 1;
+      if (tcl) {
+        const int f_nk = tr.tl_proj.nk;
+        const ArxTcLinear &L = tr.table_in_gemm ? tr.tl_proj_nt : tr.tl_proj;
+        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->J3, h->J3, h->J3, rows_f, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows_f, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows_f, ARX_ACT_RELU, w.f_img, f_nk, -1, st))) return rc;
+        if ((rc = prof_mark(h, 1, st))) return rc;
+        if ((rc = arx_tc_linear_f32(h, L, w.f_img, f_nk, rows_f, w.P, ldg, nullptr, 1, st))) return rc;
+      } else {
+        if ((rc = embed_frames(h, query_dev + b0 * h->J3, rows_f, w.H1, w.FE, st))) return rc;
+        if ((rc = prof_mark(h, 1, st))) return rc;
+        if ((rc = arx_fp32_linear(h, w.FE, h->F, tr.wp, h->F, nullptr, w.P, ldg, rows_f, ldg, h->F, ARX_ACT_NONE, nullptr, 1, st))) return rc;
+      }
+      if ((rc = arx_form_windows_launch(h, tr, w.P, nullptr, w.G, nullptr, n, false, st))) return rc;
+    } else if (tcl) {
       const int f_nk = tr.tl_proj.nk, f_onehot = tr.table_in_gemm ? f_nk - 1 : -1;
       if (from_frames) {
         if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
@@ -869,8 +892,9 @@ static int score_tcn(arx_handle *h, int ti, const float *query_dev, const float 
 // tuple images (gather + LayerNorm + exp2 pre-scale) -> [join the support chain] -> cross-attention + distances ->
 // logits / argmax -> open-set head by linearity -> fc1 -> fc2 + fc3 + sigmoid.  Replayed as two CUDA graphs (before /
 // after the join) when the arguments recur.
+// frames_stream: query_dev is a FRAME stream (n_windows + T - 1 rows of 3J); window w = frames w .. w+T-1 (arx_score_frames)
 static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
-                      float *is_true_dev, int32_t *chosen_dev, cudaStream_t st, int ep_way) {
+                      float *is_true_dev, int32_t *chosen_dev, cudaStream_t st, int ep_way, bool frames_stream = false) {
   const ArxTransformer &tr = h->tr[ti];
   const bool from_frames = query_dev != nullptr, disc = is_true_dev != nullptr;
   const int way = ep_way > 0 ? ep_way : h->way;
@@ -879,18 +903,18 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
   const bool p_embed = big_batch && (h->tc_variant & 1024) == 0 && arx_tcp_supported(h->tl_fc1) && arx_tcp_supported(h->tl_fc2);
   const int64_t chunk = pick_chunk(h, tr, way, from_frames, disc, n_windows, true, false, true, disc);
   if (ep_way > 0 && chunk < n_windows) return ARX_EP_UNSUPPORTED;
-  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, true, false, true, disc);
+  Fp32Ws sz = carve_fp32(h, tr, chunk, way, from_frames, disc, nullptr, true, false, true, disc, frames_stream);
   const size_t extra = chosen_dev ? 0 : (size_t)chunk * sizeof(int32_t) + 256;
   int rc = arx_ws_reserve(h, sz.bytes + extra);
   if (rc) return rc;
-  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, true, false, true, disc);
+  Fp32Ws w = carve_fp32(h, tr, chunk, way, from_frames, disc, h->ws, true, false, true, disc, frames_stream);
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
   h->last_path = 2;
   bool aux_pending = false;
   ArxScoreGraph *sg = nullptr;
   bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && graphs_enabled(h);     // the default streams cannot be captured
   if (capturable && capture_id(st) != 0) capturable = false;      // a caller that is capturing this stream itself gets plain launches
-  if (capturable && disc && from_frames && chunk >= n_windows && !h->prof_on && !h->trace_buf) {
+  if (capturable && disc && from_frames && !frames_stream && chunk >= n_windows && !h->prof_on && !h->trace_buf) {
     ArxScoreGraphKey key;
     key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
     key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0) | (h->query_f16 ? (1 << 22) : 0);
@@ -904,6 +928,21 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
     if ((rc = prof_mark(h, 0, st))) return rc;
     rc = score_segment(h, sg, 0, st, [&]() -> int {
       int rc = ARX_OK;
+      const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
+      if (frames_stream) {
+        // every frame is embedded and projected ONCE (position-independent); the windows are formed on the device
+        const int64_t rows_f = n + h->T - 1;
+        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->J3, h->J3, h->J3, rows_f, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc1, w.x_img, rows_f, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
+        if ((rc = arx_tc_linear_img(h, h->tl_fc2, w.h_img, rows_f, ARX_ACT_RELU, w.f_img, f_nk, -1, st))) return rc;
+        if ((rc = prof_mark(h, 1, st))) return rc;
+        if ((rc = arx_tc_linear_f32(h, tr.tl_proj_nt, w.f_img, f_nk, rows_f, w.P, g_ld, nullptr, 1, st))) return rc;
+        if (disc && (rc = arx_tc_linear_f32_small(h, tr.tl_uab, w.f_img, f_nk, rows_f, w.U, 32, nullptr, h->T, st))) return rc;
+        if ((rc = arx_form_windows_launch(h, tr, w.P, disc ? w.U : nullptr, w.G, w.uab, n, true, st))) return rc;
+        if ((rc = prof_mark(h, 2, st))) return rc;
+        if ((rc = arx_tuple_img(h, tr, w.G, g_ld / 32, n, w.kq_img, alpha, st))) return rc;
+        return ARX_OK;
+      }
       if (from_frames) {
         if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
         if (p_embed) {
@@ -915,7 +954,6 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
         }
       } else if ((rc = arx_tc_rows_to_img(h, qfeats_dev + b0 * h->T * h->F, h->F, h->F, rows, w.f_img, f_nk, f_onehot, st))) return rc;
       if ((rc = prof_mark(h, 1, st))) return rc;
-      const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
       if ((rc = arx_tcp_linear_chunked(h, tr.tl_proj, w.f_img, f_nk, rows, w.G, st))) return rc;
       if ((rc = prof_mark(h, 2, st))) return rc;
       if ((h->tc_variant & 64) == 0 && (rc = arx_tuple_img(h, tr, w.G, g_ld / 32, n, w.kq_img, alpha, st))) return rc;   // bit 6: timing only
@@ -1008,7 +1046,8 @@ static int score_fp32(arx_handle *h, int ti, const float *query_dev, const float
 
 // ep_way > 0: episode mode -- window b is scored against classes [b*ep_way, (b+1)*ep_way) of the support pool
 static int score_impl(arx_handle *h, int ti, const float *query_dev, const float *qfeats_dev, int64_t n_windows, float *logits_dev,
-                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st, int ep_way = 0) {
+                      float *is_true_dev, int32_t *chosen_dev, float *probs, float *protos, cudaStream_t st, int ep_way = 0,
+                      bool frames_stream = false) {
   if (!h->weights_loaded) return arx_fail(h, ARX_ERR_STATE, "score: weights not loaded");
   if (h->way < 1) return arx_fail(h, ARX_ERR_STATE, "score: support set not set");
   if (n_windows == 0) return ARX_OK;
@@ -1022,9 +1061,11 @@ static int score_impl(arx_handle *h, int ti, const float *query_dev, const float
   int rc = workspace_wait(h, st);
   if (rc) return rc;
   if (!debug_out && route_gen3(h, tr) && tr.ks_img)
-    rc = score_gen3(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st, ep_way);
+    rc = score_gen3(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st, ep_way, frames_stream);
   else if (!debug_out && route_tiled(h, tr))
-    rc = score_tcn(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st);
+    rc = score_tcn(h, ti, query_dev, qfeats_dev, n_windows, logits_dev, is_true_dev, chosen_dev, st, frames_stream);
+  else if (frames_stream)
+    rc = ARX_EP_UNSUPPORTED;            // the caller materialises the windows for the fp32 kernels
   else if (h->cfg.force_path == 2 && !debug_out)
     rc = arx_fail(h, ARX_ERR_INVALID, "score: force_path=2 but no tcgen05 path covers this shape (N=%d, D=%d)", tr.N, h->D);
   else {
@@ -1071,6 +1112,24 @@ int arx_score_episodes(arx_handle *h, const float *support_dev, int32_t is_featu
     } else if (rc) return rc;
   }
   return ARX_OK;
+}
+
+int arx_score_frames(arx_handle *h, const float *frames_dev, int64_t n_frames, float *logits_dev, float *is_true_dev, int32_t *chosen_dev,
+                     void *stream) {
+  if (!h || !frames_dev || !logits_dev || n_frames < 0) return arx_fail(h, ARX_ERR_INVALID, "score_frames: bad argument");
+  if (!h->cfg.has_discriminator) is_true_dev = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_windows = n_frames - h->T + 1;
+  if (n_windows <= 0) return ARX_OK;                      // fewer than seq_len frames: nothing to report (ar.py:43-44)
+  int rc = score_impl(h, 0, frames_dev, nullptr, n_windows, logits_dev, is_true_dev, chosen_dev, nullptr, nullptr, st, 0, true);
+  if (rc != ARX_EP_UNSUPPORTED) return rc;
+  // shapes on the fp32 kernels: materialise the windows, then the ordinary path
+  float *win = nullptr;
+  ARX_CUDA(h, cudaMallocAsync(reinterpret_cast<void **>(&win), (size_t)n_windows * h->T * h->J3 * sizeof(float), st));
+  if ((rc = arx_make_windows_launch(h, frames_dev, win, n_windows, st)) == ARX_OK)
+    rc = score_impl(h, 0, win, nullptr, n_windows, logits_dev, is_true_dev, chosen_dev, nullptr, nullptr, st);
+  cudaFreeAsync(win, st);
+  return rc;
 }
 
 int arx_score_features(arx_handle *h, int32_t ti, const float *qfeats_dev, int64_t n_windows, float *logits_dev, void *stream) {

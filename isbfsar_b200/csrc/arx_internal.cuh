@@ -37,6 +37,7 @@ struct ArxTransformer {
   __half *vs_img_bf = nullptr;   // Vc^T as bf16 (prototype MMA of arx_tc2.cu)
   float softmax_bound = 0.f; // static |S| bound from LayerNorm affine
   ArxTcLinear tl_proj;       // K/V projection (2cD x F) on tensor cores
+  ArxTcLinear tl_proj_nt;    // the same without the positional-table columns (frame streams: the table is added per window position)
   ArxTcLinear tl_uab;        // 32 composite columns Wdr.Wv of the second-generation head pass
   float *wc = nullptr, *tcomp = nullptr;   // composite weights (32,F) and table (T,32)
   __half *uc_img = nullptr;  // per class Wdr.Vc^T (16 x 128 fp16 B operand)
@@ -304,6 +305,10 @@ int arx_stream_frame_launch(arx_handle *h, const ArxTransformer &tr, const float
 int arx_stream_tiles_launch(arx_handle *h, const ArxTransformer &tr, const float *ring, const int *slot_next, float *G, __half *kq, cudaStream_t st);
 int arx_stream_tail_launch(arx_handle *h, const ArxTransformer &tr, const float *partial, const float *y_all, float *h1, float *logits, float *out,
                            int *slot_next, int way, cudaStream_t st);
+
+int arx_form_windows_launch(arx_handle *h, const ArxTransformer &tr, const float *P, const float *U, float *G, float *uab, int64_t n_win, bool chunked,
+                            cudaStream_t st);
+int arx_make_windows_launch(arx_handle *h, const float *frames, float *win, int64_t n_win, cudaStream_t st);
 
 // ---- tuple table (arx_tuples.cu) -------------------------------------------------
 int arx_build_tuple_table(arx_handle *h, int T, int c, int N, int32_t *out_dev, cudaStream_t st);

@@ -179,6 +179,51 @@ __global__ void __launch_bounds__(256) k_stream_tail(const float *__restrict__ h
   }
 }
 
+// Sliding windows over a frame stream (batch form): window w = frames w .. w+T-1.  From the per-frame position-independent
+// projections P (n_frames, NO) and head columns U (n_frames, 32) forms every window's per-frame projections
+//   G[w*T + t] = P[w + t] + table[t]      (table = positional encoding through the projection + biases)
+// in the chunked layout of arx_gemm_p.cu (chunked != 0: [rows/128][NO/32 chunks][128 rows][32 floats], 16-byte groups XOR-
+// swizzled by row & 7) or row-major, and  uab[w*T + t] = U[w + t] + tcomp[t].  One thread per (row, 4 columns).
+__global__ void __launch_bounds__(256) k_form_windows(const float *__restrict__ P, const float *__restrict__ U, const float *__restrict__ table,
+                                                      const float *__restrict__ tcomp, float *__restrict__ G, float *__restrict__ uab, int64_t n_win,
+                                                      int T, int NO, int chunked) {
+  const int gpr = NO / 4 + (U ? 8 : 0);                         // float4 groups per row: projections, then the 32 head columns
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_win * T * gpr) return;
+  const int64_t row = idx / gpr;
+  const int g4 = (int)(idx - row * gpr);
+  const int64_t w = row / T;
+  const int t = (int)(row - w * T);
+  if (g4 < NO / 4) {
+    const int c = g4 * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(P + (w + t) * NO + c));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(table + (size_t)t * NO + c));
+    const float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    if (chunked) {
+      const int64_t tile = row >> 7;
+      const int rr = (int)(row & 127), chunk = c >> 5, cc = c & 31;
+      float *dst = G + ((size_t)tile * (NO / 32) + chunk) * 4096 + rr * 32 + ((((cc >> 2) ^ (rr & 7)) << 2));
+      *reinterpret_cast<float4 *>(dst) = o;
+    } else {
+      *reinterpret_cast<float4 *>(G + row * NO + c) = o;
+    }
+  } else {
+    const int c = (g4 - NO / 4) * 4;
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(U + (w + t) * 32 + c));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(tcomp + (size_t)t * 32 + c));
+    *reinterpret_cast<float4 *>(uab + row * 32 + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// explicit windows (n_win, T, J3) from a frame stream: the generic route for shapes on the fp32 kernels
+__global__ void k_make_windows(const float *__restrict__ frames, float *__restrict__ win, int64_t n_win, int T, int J3) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_win * T * J3) return;
+  const int64_t w = idx / ((int64_t)T * J3);
+  const int64_t r = idx - w * T * J3;
+  win[idx] = frames[w * J3 + r];
+}
+
 }  // namespace
 
 int arx_stream_frame_launch(arx_handle *h, const ArxTransformer &tr, const float *x_dev, float *ring, int *slot_next, cudaStream_t st) {
@@ -206,6 +251,22 @@ int arx_stream_tail_launch(arx_handle *h, const ArxTransformer &tr, const float 
   k_stream_fc1<<<disc ? 32 : 1, 256, 0, st>>>(partial, y_all, h->d1_w, h->d1_b, h1, logits, K1, way, tr.N, disc);
   ARX_LAUNCH_CHECK(h);
   k_stream_tail<<<1, 256, 0, st>>>(h1, h->d2_w, h->d2_b, h->d3_w, h->d3_b, logits, out, slot_next, way, h->T, disc);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
+}
+
+int arx_form_windows_launch(arx_handle *h, const ArxTransformer &tr, const float *P, const float *U, float *G, float *uab, int64_t n_win, bool chunked,
+                            cudaStream_t st) {
+  const int NO = 2 * tr.c * h->D;
+  const int64_t total = n_win * h->T * (NO / 4 + (U ? 8 : 0));
+  k_form_windows<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, U, tr.bp, tr.tcomp, G, uab, n_win, h->T, NO, chunked ? 1 : 0);
+  ARX_LAUNCH_CHECK(h);
+  return ARX_OK;
+}
+
+int arx_make_windows_launch(arx_handle *h, const float *frames, float *win, int64_t n_win, cudaStream_t st) {
+  const int64_t total = n_win * h->T * h->J3;
+  k_make_windows<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(frames, win, n_win, h->T, h->J3);
   ARX_LAUNCH_CHECK(h);
   return ARX_OK;
 }

@@ -265,7 +265,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
           const int nvalid = p.N - (2 * qp + g) * 128;       // valid query columns of this group's tile (>= 128: all)
           for (int st = 0; st < ns; ++st, ++k) {
             const int zi = st * 128 + s;
-            float zinv = 0.f, mrow = 0.f;
+            float zinv = 0.f, mrow = 0.f, zprev = 0.f;
+            if (pass == 0 && qp > 0 && g < nw) zprev = zme[zi];   // running sum of the earlier query tiles: fetched now, used after the exponentials
             if (pass == 1 && pass0 == 0 && g < nw) {          // normaliser of this support tuple over ALL query tiles (pass A)
               if constexpr (ROWMAX) {
                 const float m0 = zme[NSP + zi], m1 = zot[NSP + zi];
@@ -348,10 +349,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
               const float zs = zl + zh;
               if (pass == 0) {
                 if constexpr (ROWMAX) {
-                  zme[zi] = qp > 0 ? zme[zi] * zscale + zs : zs;
+                  zme[zi] = qp > 0 ? zprev * zscale + zs : zs;
                   zme[NSP + zi] = mrow;
                 } else {
-                  zme[zi] = qp > 0 ? zme[zi] + zs : zs;
+                  zme[zi] = qp > 0 ? zprev + zs : zs;
                 }
                 continue;
               }

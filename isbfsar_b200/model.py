@@ -373,6 +373,28 @@ class TRXOS(nn.Module):
                           C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None, C.byref(t)), h, "arx_score_host_submit")
         return _HostTicket(self, int(t.value), q, logits, is_true)
 
+    def score_frames(self, frames):
+        """Every sliding window of seq_len consecutive frames of a frame stream (n_frames, 3J) against the current support
+        set (arx_score_frames): -> logits (n_frames-T+1, W), is_true (n_frames-T+1, 1) [None without DISC]."""
+        h = self._ensure()
+        dev = self._device()
+        lib = _lib.load()
+        x = self._f32c(frames, dev)
+        assert x.dim() == 2 and x.shape[1] == self.args.n_joints * 3, "frames must be (n_frames, 3J)"
+        B = max(0, x.shape[0] - self.args.seq_len + 1)
+        way = lib.arx_support_way(h)
+        if way < 1:
+            raise RuntimeError("score_frames: support set not set")
+        logits = torch.empty((B, way), dtype=torch.float32, device=dev)
+        is_true = torch.empty((B, 1), dtype=torch.float32, device=dev) if self.model == "DISC" else None
+        if B == 0:
+            return logits, is_true
+        with torch.cuda.device(dev):
+            _lib.check(lib.arx_score_frames(h, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(logits.data_ptr()),
+                                            C.c_void_p(is_true.data_ptr()) if is_true is not None else None, None, self._stream()),
+                       h, "arx_score_frames")
+        return logits, is_true
+
     def score_episodes(self, query, poses=None, features=None):
         """Training / evaluation call shape (train.py:110-120, compute_fsos.py:89-98): episode i scores query i
         (b,T,3J) against ITS OWN support classes, poses (b,W,T,3J) or features (b,W,T,F).  One batched pass

@@ -910,3 +910,34 @@ def test_fp16_host_rows_are_bit_identical():
     m.set_support(poses=torch.from_numpy(support[0][:5, :16]).cuda())
     with pytest.raises(ValueError):
         m.score_host(torch.zeros((4, 16, 90), dtype=torch.float16).pin_memory())
+
+
+@pytest.mark.parametrize("cfg,n_frames,path,force", [(Cfg(), 700, 2, 0), (Cfg(), 16, 2, 0), (Cfg(way=3, seq_len=8), 150, 3, 0),
+                                                     (Cfg(way=20, seq_len=32, temp_set=[2, 3]), 60, 3, 0), (Cfg(), 40, 1, 1)])
+def test_frame_stream_scoring_equals_explicit_windows(cfg, n_frames, path, force):
+    """arx_score_frames: every frame embedded / projected once, windows formed on the device -- against the same windows
+    given explicitly to arx_score and against the oracle."""
+    T = cfg.seq_len
+    m, sd = make_model(cfg, 0, force_path=force)
+    rng = np.random.default_rng(7 + n_frames)
+    support = (0.17 * rng.standard_normal((cfg.way, T, 90))).astype(np.float32)
+    frames = (0.17 * rng.standard_normal((n_frames, 90))).astype(np.float32)
+    o = min(5, n_frames - T)
+    frames[o:o + T] = support[1] + 0.05 * rng.standard_normal((T, 90)).astype(np.float32)
+    m.set_support(poses=torch.from_numpy(support).cuda())
+    F = torch.from_numpy(frames).cuda()
+    lo_s, it_s = m.score_frames(F)
+    assert m.last_path() == path
+    windows = F.unfold(0, T, 1).permute(0, 2, 1).contiguous()
+    assert lo_s.shape == (n_frames - T + 1, cfg.way)
+    lo_w, it_w = m.score(windows)
+    tol = tol_for(m)
+    assert rel_err(lo_s.cpu(), lo_w.cpu()).max() < tol and rel_err(it_s.cpu(), it_w.cpu()).max() < tol
+    k = min(48, windows.shape[0])
+    lo, it = TrxOracle(cfg, sd).score(support[None], np.arange(cfg.way)[None], windows[:k].cpu().numpy(), chunk=16)
+    assert rel_err(lo_s[:k].cpu(), lo).max() < tol and rel_err(it_s[:k].cpu(), it).max() < tol
+    assert np.array_equal(lo_s[:k].argmax(1).cpu().numpy(), lo.argmax(1))
+    assert int(lo_s[o].argmax()) == 1
+    # fewer than seq_len frames: nothing to score
+    e_lo, e_it = m.score_frames(F[:T - 1])
+    assert e_lo.shape == (0, cfg.way)
