@@ -231,7 +231,8 @@ ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t
  *         instead of MUFU.EX2 (0 = none (default), 2, 3, 4; measured: no gain on B200, the packed FMA ops cost
  *         as much pipe time as the MUFU they replace).
  *  key 5: CUDA-graph replay of the arx_score kernel chain when its arguments recur (default on; the environment
- *         variable ARX_GRAPHS=0 disables it too). */
+ *         variable ARX_GRAPHS=0 disables it too).
+ *  key 6: tiled attention kernels, normaliser pass: half of the exponentials on the FMA pipe (default 1; 0 = all on the MUFU). */
 ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
 /* key 1 (value != 0) arms a timeline trace of CTA 0 of the attention kernel; this reads it back:
  * host_out[3 roles][64 tiles][8 stamps] of SM clock values (bring-up tool). */

@@ -1540,6 +1540,7 @@ int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
   if (key == 3) { h->attn_stagger = (int)value; return ARX_OK; }
   if (key == 4) { h->attn_poly = (int)value; return ARX_OK; }
   if (key == 5) { h->graphs_on = value != 0; return ARX_OK; }
+  if (key == 6) { h->tcn_poly = value != 0; return ARX_OK; }
   if (key == 1) {   // allocate (value != 0) / free the kernel timeline trace buffer: 3 roles x 64 tiles x 8 stamps
     if (value && !h->trace_buf) {
       ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->trace_buf), 3 * 64 * 8 * sizeof(long long)));

@@ -163,6 +163,7 @@ struct arx_handle {
   size_t zscratch_bytes = 0;
   ArxStream stream;
   uint64_t tiles_gen[ARX_MAX_TRANSFORMERS] = {0, 0, 0, 0};   // support generation the tiled operands were built for (+1)
+  int tcn_poly = 1;                 // tiled attention, pass A: half of the exponentials on the FMA pipe (debug key 6)
   int *tcn_diag = nullptr;          // watchdog record of the tiled attention kernel
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)

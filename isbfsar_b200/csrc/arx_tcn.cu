@@ -61,6 +61,7 @@ struct AttnNParams {
   float *zscratch;          // [grid][2 unit parity][2 groups][2: Z | M][ns*128]
   int *diag;                // watchdog record (see mbar_wait_wd)
   int n_win, way, N, T, c, nq, ns, tab_ld, tab_off, tab_pstride, mode, L, y_nk;
+  int poly;                 // pass A: every other register pair takes the FMA-pipe exp2 polynomial
   int same_window;          // mode 1: every unit scores window 0 (against class chosen[u]); y row = u (streaming: the head of ALL classes at once)
 };
 
@@ -91,6 +92,23 @@ __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// exp2 of two pre-scaled scores on the FMA pipe instead of the MUFU: round-to-nearest split x = n + f with the 1.5*2^23 magic
+// constant, 2^f on [-0.5, 0.5] by a degree-3 polynomial (max relative error 7.5e-5), exponent add by an integer shift-add.
+// Used for every other register pair of PASS A only: there the tile is summed, not stored, the FMA pipe is idle, and the MUFU
+// (16 lanes/clk/SM) is the limiter -- in the single-pass N=120 kernel the same trick gained nothing because the FMA pipe was
+// already busy with scaling and stores.  |x| < 100 by the LayerNorm bound (or after the row-max shift).
+__device__ __forceinline__ void exp2_poly2(uint32_t &a, uint32_t &b) {
+  const uint64_t MAGIC = pack2(12582912.0f, 12582912.0f);
+  const uint64_t x = pack2u(a, b);
+  const uint64_t t = add2(x, MAGIC);
+  const uint64_t f = sub2(x, sub2(t, MAGIC));
+  uint64_t p2 = fma2(f, pack2(0.0551716685f, 0.0551716685f), pack2(0.2426111251f, 0.2426111251f));
+  p2 = fma2(p2, f, pack2(0.6932609677f, 0.6932609677f));
+  p2 = fma2(p2, f, pack2(0.9999280572f, 0.9999280572f));
+  a = (uint32_t)p2 + ((uint32_t)t << 23);
+  b = (uint32_t)(p2 >> 32) + ((uint32_t)(t >> 32) << 23);
 }
 
 template <bool ROWMAX>
@@ -327,8 +345,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
                 r[j] = (uint32_t)v; r[j + 1] = (uint32_t)(v >> 32);
               }
             }
+            if (pass == 0 && p.poly) {
 #pragma unroll
-            for (int j = 0; j < 128; ++j) r[j] = ex2_bits(r[j]);
+              for (int j = 0; j < 128; j += 4) {
+                exp2_poly2(r[j], r[j + 1]);
+                r[j + 2] = ex2_bits(r[j + 2]); r[j + 3] = ex2_bits(r[j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 128; ++j) r[j] = ex2_bits(r[j]);
+            }
             mbar_arrive(&bars[B_XU + g]);
             if (pass == 0 || pass0 == 1) {
               // row sum over the valid query columns (pad columns of the last tile have S = 0, exp = 1: masked out)
@@ -693,6 +719,7 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
     h->zscratch_bytes = zbytes;
   }
   p.zscratch = h->zscratch + (p.mode == 1 ? zhalf : 0);
+  p.poly = (h->tcn_poly && p.ns >= 8) ? 1 : 0;      // measured on B200: +3.4 % at N=4960 (MUFU-bound pass), -5 % at N=496 (latency-bound)
   if (!h->tcn_diag) {
     ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->tcn_diag), 8 * sizeof(int)));
     ARX_CUDA(h, cudaMemset(h->tcn_diag, 0, 8 * sizeof(int)));
