@@ -816,7 +816,7 @@ def main():
                     "SURVEY 8d allows 'outputs only' when fused behind the attention; as built the winning class's tile is recomputed from the Kq image"),
         ]
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # the CPU arm is timed at N=1 only (the other ranks' processes share the host cores)
             cpu = cpu_baseline(cfg, sd, support0, labels, query, args.cpu_seconds, os.cpu_count() or 1)
         extras = None
         if not args.no_extras and world == 1:
