@@ -232,7 +232,8 @@ ARX_API int arx_profile_read(arx_handle *h, double *ms, int64_t *chunks, int32_t
  *         as much pipe time as the MUFU they replace).
  *  key 5: CUDA-graph replay of the arx_score kernel chain when its arguments recur (default on; the environment
  *         variable ARX_GRAPHS=0 disables it too).
- *  key 6: tiled attention kernels, normaliser pass: half of the exponentials on the FMA pipe (default 1; 0 = all on the MUFU). */
+ *  key 6: tiled attention kernels, normaliser pass: half of the exponentials on the FMA pipe (default 1; 0 = all on the MUFU).
+ *  key 7: tiled attention kernels, normaliser pass: softmax groups free-running (default 1) instead of taking turns on the MUFU. */
 ARX_API int arx_debug_set(arx_handle *h, int32_t key, int32_t value);
 /* key 1 (value != 0) arms a timeline trace of CTA 0 of the attention kernel; this reads it back:
  * host_out[3 roles][64 tiles][8 stamps] of SM clock values (bring-up tool). */

@@ -231,7 +231,7 @@ void arx_destroy(arx_handle *h) {
   for (int i = 0; i < ARX_MAX_TRANSFORMERS; ++i) {
     ArxTransformer &tr = h->tr[i];
     cudaFree(tr.pe); cudaFree(tr.wp); cudaFree(tr.bp); cudaFree(tr.ln_g); cudaFree(tr.ln_b); cudaFree(tr.tuples); cudaFree(tr.bp_sums); cudaFree(tr.wp_ext);
-    cudaFree(tr.tup_packed);
+    cudaFree(tr.tup_packed); cudaFree(tr.sel_tiles);
   }
   cudaFree(h->dr_w); cudaFree(h->dr_b); cudaFree(h->d1_w); cudaFree(h->d1_b);
   cudaFree(h->d2_w); cudaFree(h->d2_b); cudaFree(h->d3_w); cudaFree(h->d3_b);
@@ -761,7 +761,7 @@ template <class F> static int score_segment(arx_handle *h, ArxScoreGraph *g, int
 
 // ---- scoring on the tiled any-N tcgen05 kernels (arx_tcn.cu) -----------------------------------------------------
 struct TcnWs {
-  __half *x_img, *h_img, *f_img, *kq, *y_img, *h1_img;
+  __half *x_img, *h_img, *f_img, *kq, *y_img, *h1_img, *vq, *vq_head;
   float *H1, *FE, *G, *partial, *uab, *y, *h1, *h2, *P;
   size_t bytes;
 };
@@ -779,6 +779,9 @@ static TcnWs carve_tcn(arx_handle *h, const ArxTransformer &tr, int64_t n, int w
   w.G = c.take<float>(rows_pad * 2 * tr.c * h->D);
   w.kq = c.take<__half>((size_t)n * nq * 128 * 128);
   w.partial = c.take<float>(n * way * 4);
+  const int nsel = (2 * tr.c * h->T + 63) / 64;                     // selection operands: 16 KB sub-tiles per window
+  w.vq = c.take<__half>((size_t)n * nsel * 8192);
+  w.vq_head = disc ? c.take<__half>((size_t)n * nsel * 8192) : nullptr;
   if (disc) {
     const int64_t K1 = (int64_t)tr.N * h->T;
     w.uab = c.take<float>(rows * 64 + 256);
@@ -804,12 +807,12 @@ static int tcn_backend(arx_handle *h, const ArxTransformer &tr, const TcnWs &w, 
   if ((rc = support_wait(h, st))) return rc;          // tup_packed and the class tiles come from the support chain
   if ((rc = arx_tcn_prep_query(h, tr, w.G, ldg, n, w.kq, st))) return rc;
   if ((rc = prof_mark(h, 3, st))) return rc;
-  if ((rc = arx_tcn_attention(h, tr, w.kq, w.G, ldg, n, way, w.partial, logits, ch, st))) return rc;
+  if ((rc = arx_tcn_attention(h, tr, w.kq, w.G, ldg, n, way, w.partial, logits, ch, w.vq, st))) return rc;
   if ((rc = prof_mark(h, 4, st))) return rc;
   if (is_true) {
     if (tcl && ((int64_t)tr.N * h->T) % 64)       // fc1's K is padded to whole 64-column sub-tiles: the pad columns must be zero, not stale
       ARX_CUDA(h, cudaMemsetAsync(w.y_img, 0, (size_t)((n + 127) / 128 * 128) * h->tl_d1.nk * 64 * sizeof(__half), st));
-    if ((rc = arx_tcn_head(h, tr, w.kq, w.G, ldg, n, ch, w.uab, w.y, w.y_img, tcl ? h->tl_d1.nk : 0, st))) return rc;
+    if ((rc = arx_tcn_head(h, tr, w.kq, w.G, ldg, n, ch, w.uab, w.y, w.y_img, tcl ? h->tl_d1.nk : 0, w.vq_head, st))) return rc;
     if (tcl) {
       if ((rc = arx_tc_linear_img(h, h->tl_d1, w.y_img, n, ARX_ACT_RELU, w.h1_img, h->tl_d2.nk, -1, st))) return rc;
       if ((rc = arx_tc_linear_sigmoid_dot(h, h->tl_d2, w.h1_img, n, h->d3_w, h->d3_b, is_true, st))) return rc;
@@ -1409,10 +1412,10 @@ int arx_stream_push(arx_handle *h, const float *frame_host, float *result_host, 
     if (disc) {
       ARX_CUDA(h, cudaEventRecord(s.ev_fork, s.st));
       ARX_CUDA(h, cudaStreamWaitEvent(s.st2, s.ev_fork, 0));
-      if ((rc = arx_tcn_head_all(h, tr, w.kq, w.G, ldg, way, s.iota, w.uab, s.y_all, s.st2))) return rc;
+      if ((rc = arx_tcn_head_all(h, tr, w.kq, w.G, ldg, way, s.iota, w.uab, s.y_all, w.vq_head, s.st2))) return rc;
       ARX_CUDA(h, cudaEventRecord(s.ev_join, s.st2));
     }
-    if ((rc = arx_tcn_attention_partial(h, tr, w.kq, w.G, ldg, 1, way, w.partial, s.st))) return rc;
+    if ((rc = arx_tcn_attention_partial(h, tr, w.kq, w.G, ldg, 1, way, w.partial, w.vq, s.st))) return rc;
     if ((rc = prof_mark(h, 4, s.st))) return rc;
     if (disc) ARX_CUDA(h, cudaStreamWaitEvent(s.st, s.ev_join, 0));
     if ((rc = arx_stream_tail_launch(h, tr, w.partial, s.y_all, w.h1, s.logits, s.out_dev, s.slot, way, s.st))) return rc;
@@ -1541,6 +1544,7 @@ int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
   if (key == 4) { h->attn_poly = (int)value; return ARX_OK; }
   if (key == 5) { h->graphs_on = value != 0; return ARX_OK; }
   if (key == 6) { h->tcn_poly = value != 0; return ARX_OK; }
+  if (key == 7) { h->tcn_free_a = value != 0; return ARX_OK; }
   if (key == 1) {   // allocate (value != 0) / free the kernel timeline trace buffer: 3 roles x 64 tiles x 8 stamps
     if (value && !h->trace_buf) {
       ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->trace_buf), 3 * 64 * 8 * sizeof(long long)));

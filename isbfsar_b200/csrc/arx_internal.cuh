@@ -44,6 +44,7 @@ struct ArxTransformer {
   // tiled operands of the any-N kernel (arx_tcn.cu): [way][Npad/128] 32 KB tiles
   __half *kc_tiles = nullptr, *vct_tiles = nullptr, *uc_tiles = nullptr;
   uint32_t *tup_packed = nullptr;   // (N) tuple frames packed one byte each
+  __half *sel_tiles = nullptr;      // one-hot frame-selection operand of every query tile (selection MMA of arx_tcn.cu)
 };
 
 // Replayable CUDA graphs of the arx_score kernel chain for one (buffers, batch, support geometry, weights) key: the
@@ -163,6 +164,7 @@ struct arx_handle {
   size_t zscratch_bytes = 0;
   ArxStream stream;
   uint64_t tiles_gen[ARX_MAX_TRANSFORMERS] = {0, 0, 0, 0};   // support generation the tiled operands were built for (+1)
+  int tcn_free_a = 1;               // tiled attention, pass A: softmax groups free-running (debug key 7)
   int tcn_poly = 1;                 // tiled attention, pass A: half of the exponentials on the FMA pipe (debug key 6)
   int *tcn_diag = nullptr;          // watchdog record of the tiled attention kernel
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
@@ -292,14 +294,14 @@ bool arx_tcn_needs_rowmax(const ArxTransformer &tr);
 int arx_tcn_prep_support(arx_handle *h, ArxTransformer &tr, int way, bool with_head, cudaStream_t st);
 int arx_tcn_prep_query(arx_handle *h, const ArxTransformer &tr, const float *G, int ldg, int64_t n_win, __half *kq_tiles, cudaStream_t st);
 int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
-                      float *partial, float *logits, int32_t *chosen, cudaStream_t st);
+                      float *partial, float *logits, int32_t *chosen, __half *vq_ws, cudaStream_t st);
 int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
-                 float *uab, float *y, __half *y_img, int y_nk, cudaStream_t st);
+                 float *uab, float *y, __half *y_img, int y_nk, __half *vq_ws, cudaStream_t st);
 
 int arx_tcn_head_all(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int way, const int32_t *iota,
-                     float *uab, float *y_all, cudaStream_t st);
+                     float *uab, float *y_all, __half *vq_ws, cudaStream_t st);
 int arx_tcn_attention_partial(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
-                              float *partial, cudaStream_t st);
+                              float *partial, __half *vq_ws, cudaStream_t st);
 
 // ---- streaming kernels (arx_stream.cu)
 int arx_stream_frame_launch(arx_handle *h, const ArxTransformer &tr, const float *x_dev, float *ring, int *slot_next, cudaStream_t st);

@@ -13,8 +13,10 @@
 //             lane == support tuple s) accumulated into Z[st*128+s]
 //   pass B  same tiles again: exp2 recomputed, P = E / Z[s] written to shared memory as the MN-major bf16 B operand,
 //             MMA2  proto^T[d, q] += Vc^T[st][d, :] . P[q, :]   accumulated over st in TMEM (one accumulator per query
-//             tile of the pair); after the last st the epilogue warps form  sum_q (Vq[q][d] - proto[q][d])^2  with
-//             Vq[q][d] = sum_p Gv_p[frame_p(q)][d] rebuilt from the per-frame V projections (tuple features never exist).
+//             tile of the pair).  The accumulator does not start at zero but at -Vq^T: a SELECTION MMA  -Gv^T[d, (p,t)] .
+//             Sel[q, (p,t)]^T  (one-hot rows: frame p of tuple q is t; Gv as hi + lo fp16 halves, K = 2cT) rebuilds
+//             Vq[q][d] = sum_p Gv_p[frame_p(q)][d] on the tensor core, so after the last st the epilogue warps only form
+//             sum_q acc[d][q]^2 -- no table, no gather (tuple features never exist; pad columns come out exactly 0).
 // N <= 128 (one query tile) needs no pass A: the row sum of the only tile is the normaliser.
 // The exponentials are computed twice (1.67x the exps of a single pass would need E kept on chip: N=496 alone is
 // 512 KB of bf16 per class); MUFU.EX2 stays the co-limiting pipe exactly as in the N=120 kernel.
@@ -52,15 +54,19 @@ struct AttnNParams {
   const __half *kq_img;     // [n_win][nq] 32 KB tiles, K-major SW128, rows = query tuples (LayerNorm-ed, pre-scaled by log2e/sqrt(D))
   const __half *kc_img;     // [classes][ns] tiles, rows = support tuples
   const __half *vct_img;    // [classes][ns] tiles, rows = d (mode 0: Vc^T) or l (mode 1: Uc), cols = support tuples, bf16
-  const float *tab;         // per-frame table, row (win*T + t): part p of lane x at tab[row*tab_ld + tab_off + p*tab_pstride + x]
-  const uint32_t *tup;      // [N] tuple frames packed i | j << 8 | k << 16
+  const __half *vq_img;     // [windows][nsel] 16 KB sub-tiles (128 rows x 64, fp16 K-major SW128): MINUS the per-frame table of the
+                            // window, hi | lo halves, column h*c*T + p*T + t; rows = d (mode 0: V projections) or l (mode 1: head table)
+  const __half *sel_img;    // [nq][nsel] 16 KB sub-tiles (128 query rows x 64): one-hot frame selection of every tuple, both halves
+  int nsel;                 // 64-column sub-tiles of the selection operands = ceil(2*c*T / 64)
   const int32_t *chosen;    // mode 1: class of every window
   float *partial;           // mode 0: [n_win*way][4] squared-distance partials (one per epilogue warp)
   float *y;                 // mode 1: fp32 [n_win][N*L], or
   __half *y_img;            //         fp16 activation image [ceil(n_win/128)][y_nk][128 x 64]
   float *zscratch;          // [grid][2 unit parity][2 groups][2: Z | M][ns*128]
   int *diag;                // watchdog record (see mbar_wait_wd)
-  int n_win, way, N, T, c, nq, ns, tab_ld, tab_off, tab_pstride, mode, L, y_nk;
+  long long *trace;         // optional timeline of CTA 0 (bring-up tool): [3 roles][64 steps][8 stamps] of clock64
+  int n_win, way, N, T, c, nq, ns, mode, L, y_nk;
+  int free_a;               // pass A: the softmax groups run free instead of taking turns on the MUFU phase
   int poly;                 // pass A: every other register pair takes the FMA-pipe exp2 polynomial
   int same_window;          // mode 1: every unit scores window 0 (against class chosen[u]); y row = u (streaming: the head of ALL classes at once)
 };
@@ -81,6 +87,7 @@ __device__ __forceinline__ void mbar_wait_wd_(uint64_t *bar, uint32_t parity, in
     }
   }
 }
+#define TRACEN(role, step, slot) do { if (p.trace && blockIdx.x == 0 && (step) < 64) p.trace[(((role) * 64) + (step)) * 8 + (slot)] = clock64(); } while (0)
 #define mbar_wait_wd(bar, parity) mbar_wait_wd_((bar), (parity), p.diag, (int)((bar) - bars) | (__LINE__ << 8))
 
 __device__ __forceinline__ uint32_t ex2_bits(uint32_t x) {
@@ -147,30 +154,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
     setmaxnreg_dec<40>();
     if (warp == 0) {
       if (elect_one()) {            // producer: class operands -- Kc every step (single-buffered), Vc^T/Uc in pass B (2-stage ring)
-        int k = 0, kb = 0;
+        int k = 0, kr = 0;                     // kr: items of the Vc ring (selection operands and Vc^T tiles alike)
         for (int ui = 0; ui < my_units; ++ui) {
           const int u = blockIdx.x + ui * gridDim.x;
           const size_t cls = head ? (size_t)p.chosen[u] : (size_t)(u % p.way);
+          const size_t win = head ? (p.same_window ? 0 : (size_t)u) : (size_t)(u / p.way);
           const uint8_t *kc0 = reinterpret_cast<const uint8_t *>(p.kc_img) + cls * ns * IMG_BYTES;
           const uint8_t *vc0 = reinterpret_cast<const uint8_t *>(p.vct_img) + cls * ns * IMG_BYTES;
+          const uint8_t *vq0 = reinterpret_cast<const uint8_t *>(p.vq_img) + win * p.nsel * SUB_BYTES;
           for (int pass = pass0; pass < 2; ++pass)
-            for (int qp = 0; qp < nqp; ++qp)
+            for (int qp = 0; qp < nqp; ++qp) {
               for (int st = 0; st < ns; ++st, ++k) {
                 const uint8_t *kc = kc0 + (size_t)st * IMG_BYTES;
                 mbar_wait_wd(&bars[B_EMPTY_KC], (k & 1) ^ 1);
                 mbar_arrive_expect_tx(&bars[B_FULL_KC], IMG_BYTES);
                 bulk_g2s(smem + OFF_KC, kc, SUB_BYTES, &bars[B_FULL_KC]);
                 bulk_g2s(smem + OFF_KC + SUB_BYTES, kc + SUB_BYTES, SUB_BYTES, &bars[B_FULL_KC]);
+                if (pass == 1 && st == 0) {
+                  // selection operands of the pair's tiles: [ -Gv^T sub-tile j | Sel sub-tile j of the query tile ] per ring item.
+                  // Issued AFTER the first Kc of the pair: the ring only drains once the epilogue has released the accumulators,
+                  // and MMA1 of the new pair must not wait behind that.
+                  const int nw = min(2, nq - 2 * qp);
+                  for (int w = 0; w < nw; ++w)
+                    for (int j = 0; j < p.nsel; ++j, ++kr) {
+                      const int sg = kr & 1;
+                      mbar_wait_wd(&bars[B_EMPTY_VC + sg], ((kr >> 1) & 1) ^ 1);
+                      mbar_arrive_expect_tx(&bars[B_FULL_VC + sg], IMG_BYTES);
+                      bulk_g2s(smem + OFF_VCT + sg * IMG_BYTES, vq0 + (size_t)j * SUB_BYTES, SUB_BYTES, &bars[B_FULL_VC + sg]);
+                      bulk_g2s(smem + OFF_VCT + sg * IMG_BYTES + SUB_BYTES,
+                               reinterpret_cast<const uint8_t *>(p.sel_img) + ((size_t)(2 * qp + w) * p.nsel + j) * SUB_BYTES, SUB_BYTES,
+                               &bars[B_FULL_VC + sg]);
+                    }
+                }
                 if (pass == 1) {
                   const uint8_t *vc = vc0 + (size_t)st * IMG_BYTES;
-                  const int sg = kb & 1;
-                  mbar_wait_wd(&bars[B_EMPTY_VC + sg], ((kb >> 1) & 1) ^ 1);
+                  const int sg = kr & 1;
+                  mbar_wait_wd(&bars[B_EMPTY_VC + sg], ((kr >> 1) & 1) ^ 1);
                   mbar_arrive_expect_tx(&bars[B_FULL_VC + sg], IMG_BYTES);
                   bulk_g2s(smem + OFF_VCT + sg * IMG_BYTES, vc, SUB_BYTES, &bars[B_FULL_VC + sg]);
                   bulk_g2s(smem + OFF_VCT + sg * IMG_BYTES + SUB_BYTES, vc + SUB_BYTES, SUB_BYTES, &bars[B_FULL_VC + sg]);
-                  ++kb;
+                  ++kr;
                 }
               }
+            }
         }
       }
     } else if (warp == 2) {
@@ -206,11 +232,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
             for (int qp = 0; qp < nqp; ++qp, ++kq) {
               const int nw = min(2, nq - 2 * qp);
               const uint32_t idesc = nw == 2 ? idesc_f16(128, 256, 0, 0) : idesc_f16(128, 128, 0, 0);
+              TRACEN(0, k, 3);
               mbar_wait_wd(&bars[B_FULL_KQ], kq & 1);
+              TRACEN(0, k, 4);
               for (int st = 0; st < ns; ++st, ++k) {
+                TRACEN(0, k, 0);
                 mbar_wait_wd(&bars[B_FULL_KC], k & 1);
+                TRACEN(0, k, 1);
                 mbar_wait_wd(&bars[B_S_EMPTY], (k & 1) ^ 1);
                 tc_fence_after();
+                TRACEN(0, k, 2);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                   const uint32_t aoff = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
@@ -229,22 +260,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
         constexpr uint64_t DESC_MN = smem_desc_sw128(16384, 1024);
         constexpr uint32_t IDESC2 = idesc_bf16(128, 128, 0, 1);
         const uint32_t sbase = smem_u32(smem);
-        int kb = 0, ke = 0;
+        constexpr uint32_t IDESC_SEL = idesc_f16(128, 128, 0, 0);
+        int kb = 0, kr = 0, ke = 0;
         for (int ui = 0; ui < my_units; ++ui)
           for (int qp = 0; qp < nqp; ++qp, ++ke) {
             const int nw = min(2, nq - 2 * qp);
-            for (int st = 0; st < ns; ++st, ++kb) {
-              const int sg = kb & 1;
-              mbar_wait_wd(&bars[B_FULL_VC + sg], (kb >> 1) & 1);
+            // the accumulators of the pair start at -Vq^T (selection MMA), once the epilogue has drained the previous pair's
+            for (int w = 0; w < nw; ++w) {
+              mbar_wait_wd(&bars[B_O_EMPTY + w], (ke & 1) ^ 1);
+              for (int j = 0; j < p.nsel; ++j, ++kr) {
+                const int sg = kr & 1;
+                mbar_wait_wd(&bars[B_FULL_VC + sg], (kr >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  mma_f16_ss(TM_O + w * 128, smem_desc_at(DESC_K, sbase + OFF_VCT + sg * IMG_BYTES + kk * 32),
+                             smem_desc_at(DESC_K, sbase + OFF_VCT + sg * IMG_BYTES + SUB_BYTES + kk * 32), IDESC_SEL, (j > 0 || kk > 0) ? 1u : 0u);
+                mma_commit(&bars[B_EMPTY_VC + sg]);
+              }
+            }
+            if (nw == 1) mbar_wait_wd(&bars[B_O_EMPTY + 1], (ke & 1) ^ 1);      // the absent slot's barriers stay in phase (see below)
+            for (int st = 0; st < ns; ++st, ++kb, ++kr) {
+              const int sg = kr & 1;
+              mbar_wait_wd(&bars[B_FULL_VC + sg], (kr >> 1) & 1);
               for (int w = 0; w < nw; ++w) {
                 mbar_wait_wd(&bars[B_P_FULL + w], kb & 1);
-                if (st == 0) mbar_wait_wd(&bars[B_O_EMPTY + w], (ke & 1) ^ 1);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                   const uint32_t off = (kk >> 2) * SUB_BYTES + (kk & 3) * 32;
                   mma_f16_ss(TM_O + w * 128, smem_desc_at(DESC_K, sbase + OFF_VCT + sg * IMG_BYTES + off),
-                             smem_desc_at(DESC_MN, sbase + OFF_P + w * IMG_BYTES + kk * 2048), IDESC2, (st > 0 || kk > 0) ? 1u : 0u);
+                             smem_desc_at(DESC_MN, sbase + OFF_P + w * IMG_BYTES + kk * 2048), IDESC2, 1u);
                 }
                 if (st == ns - 1) mma_commit(&bars[B_O_FULL + w]);
                 mma_commit(&bars[B_P_EMPTY + w]);
@@ -252,7 +298,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
               if (nw == 1) {        // unpaired tile: slot 1's barriers complete the same phases, sequenced like a real tile (an
                                     // mbarrier parity wait cannot tell phase k from k+2: nothing may run two phases ahead of its waiter)
                 mbar_wait_wd(&bars[B_P_FULL + 1], kb & 1);
-                if (st == 0) mbar_wait_wd(&bars[B_O_EMPTY + 1], (ke & 1) ^ 1);
                 if (st == ns - 1) mbar_arrive(&bars[B_O_FULL + 1]);
                 mbar_arrive(&bars[B_P_EMPTY + 1]);
               }
@@ -269,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint8_t *prow = smem + OFF_P + g * IMG_BYTES + (s >> 3) * 1024 + (s & 7) * 128;
     const int NSP = ns * 128;
-    int k = 0, kb = 0;
+    int k = 0, kb = 0, kt = 0;               // kt: steps that took the MUFU token
     for (int ui = 0; ui < my_units; ++ui) {
       float *zme = p.zscratch + ((((size_t)blockIdx.x * 2 + (ui & 1)) * 2 + g) * 2) * NSP;      // this group's [Z | M]
       const float *zot = p.zscratch + ((((size_t)blockIdx.x * 2 + (ui & 1)) * 2 + (g ^ 1)) * 2) * NSP;
@@ -283,6 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
           const int nvalid = p.N - (2 * qp + g) * 128;       // valid query columns of this group's tile (>= 128: all)
           for (int st = 0; st < ns; ++st, ++k) {
             const int zi = st * 128 + s;
+            const bool tok = pass == 1 || !p.free_a;
             // everything this step needs from the normaliser scratch is FETCHED here and USED after the exponentials: a global
             // load whose value is consumed right away sits on the softmax critical path (measured: +18 % on triples for zprev alone)
             float zinv = 0.f, mrow = 0.f, zprev = 0.f, za = 0.f, zb = 0.f, ma = 0.f, mb = 0.f;
@@ -291,12 +337,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
               za = zme[zi]; zb = zot[zi];
               if constexpr (ROWMAX) { ma = zme[NSP + zi]; mb = zot[NSP + zi]; }
             }
+            const bool trc = (threadIdx.x == 128 + g * 128);
+            if (trc) TRACEN(1 + g, k, 0);
             mbar_wait_wd(&bars[B_S_FULL], k & 1);
             tc_fence_after();
+            if (trc) TRACEN(1 + g, k, 1);
             if (g >= nw) {              // unpaired tile: this group has no columns, but its barriers keep their phase, in turn
               mbar_arrive(&bars[B_S_EMPTY]);
-              mbar_wait_wd(&bars[B_XU + 0], k & 1);
-              mbar_arrive(&bars[B_XU + 1]);
+              if (tok) {
+                mbar_wait_wd(&bars[B_XU + 0], kt & 1);
+                mbar_arrive(&bars[B_XU + 1]);
+                ++kt;
+              }
               if (pass == 1) {          // sequenced like a real P tile: without the wait this barrier could complete two
                                         // phases while the MMA2 issuer is held up behind a slow epilogue (seen on the GPU)
                 mbar_wait_wd(&bars[B_P_EMPTY + 1], (kb & 1) ^ 1);
@@ -314,8 +366,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
             tc_fence_before();
             mbar_arrive(&bars[B_S_EMPTY]);
             // MUFU token: the groups take turns on the exp phase so that one's loads / sums / stores run under the other's MUFU stream
-            if (g == 0) { if (k > 0) mbar_wait_wd(&bars[B_XU + 1], (k - 1) & 1); }
-            else mbar_wait_wd(&bars[B_XU + 0], k & 1);
+            // (pass B only: in the normaliser pass a group has nothing but loads and sums around its exponentials, and two warps
+            // per scheduler issuing MUFU together run the pipe at 8 clk per instruction instead of ~11 for one -- p.free_a)
+            if (tok) {
+              if (g == 0) { if (kt > 0) mbar_wait_wd(&bars[B_XU + 1], (kt - 1) & 1); }
+              else mbar_wait_wd(&bars[B_XU + 0], kt & 1);
+            }
+            if (trc) TRACEN(1 + g, k, 2);
             float zscale = 0.f;             // ROWMAX pass A: factor that brings the running sum to the new maximum
             if constexpr (ROWMAX) {
               if (pass == 1 && pass0 == 0) mrow = fmaxf(ma, mb);
@@ -353,7 +410,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
 #pragma unroll
               for (int j = 0; j < 128; ++j) r[j] = ex2_bits(r[j]);
             }
-            mbar_arrive(&bars[B_XU + g]);
+            if (tok) { mbar_arrive(&bars[B_XU + g]); ++kt; }
+            if (trc) TRACEN(1 + g, k, 3);
             if (pass == 0 || pass0 == 1) {
               // row sum over the valid query columns (pad columns of the last tile have S = 0, exp = 1: masked out)
               if (nvalid < 128) {
@@ -384,9 +442,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
             } else {
               if constexpr (ROWMAX) zinv = __frcp_rn(za * ex2f(ma - mrow) + zb * ex2f(mb - mrow)) * 1.0028177f;
               else zinv = __frcp_rn(za + zb) * 1.0028177f;      // centred truncation to bf16, see arx_tc2.cu
+              if (nvalid < 128) {           // pad query columns of the last tile: P = 0, so their accumulator columns stay exactly 0
+#pragma unroll
+                for (int j = 0; j < 128; ++j) r[j] = j < nvalid ? r[j] : 0u;
+              }
             }
             const uint64_t zz = pack2(zinv, zinv);
+            if (trc) TRACEN(1 + g, k, 4);
             mbar_wait_wd(&bars[B_P_EMPTY + g], (kb & 1) ^ 1);
+            if (trc) TRACEN(1 + g, k, 5);
 #pragma unroll
             for (int c16 = 0; c16 < 16; ++c16) {
               uint32_t hh[4];
@@ -399,6 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
             }
             fence_proxy_async_smem();
             mbar_arrive(&bars[B_P_FULL + g]);
+            if (trc) TRACEN(1 + g, k, 6);
             ++kb;
           }
         }
@@ -406,69 +471,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
     }
   } else {
     // ---------------- epilogue warps: thread == TMEM lane == output dimension d (mode 0) or head column l (mode 1)
-    // Vq[q][lane] = sum_p tab_p[frame_p(q)][lane] is gathered from the per-frame table (L1/L2 resident, 128-byte coalesced
-    // rows) one 32-column chunk AHEAD of the accumulator chunk it is compared with: the tuple words of a chunk are one
-    // coalesced load, broadcast by shuffles, and all table loads of a chunk are issued back to back (no dependent chains --
-    // a first version that loaded per column ran at ~150 K clk per tile and throttled the whole kernel).
+    // The accumulator already holds proto - Vq (mode 0) or sum_s P.Uc - head table (mode 1): see the selection MMA.  Earlier
+    // versions rebuilt Vq here from a per-frame table in global memory: even with the loads of a chunk batched the register
+    // budget kept only a few in flight, a tile took 18-41 K clk (timeline trace, tools/trace_tcn.py) and stalled the next tile
+    // pair's first MMA2 behind O_EMPTY -- at N=496 the epilogue cost as much as the sixteen steps of the unit; a thread-private
+    // table in local memory was slower still (L1 is what shared memory leaves: nothing).
     setmaxnreg_inc<152>();
     const int quad = warp & 3;
     const int d = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const bool c3 = p.c == 3;
-    const size_t ld = (size_t)p.tab_ld;
-    const int ps = p.tab_pstride;
     int ke = 0;
     for (int ui = 0; ui < my_units; ++ui) {
       const int u = blockIdx.x + ui * gridDim.x;
       const int win = head ? u : u / p.way;                    // output row
-      const float *tb = p.tab + (size_t)(head && p.same_window ? 0 : win) * p.T * p.tab_ld + p.tab_off + d;
-      auto gather = [&](int qc, float (&v)[32]) {        // Vq of columns qc .. qc+31 (clamped: pad columns are masked later)
-        const uint32_t tpl = __ldg(p.tup + min(qc + lane, p.N - 1));
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const uint32_t tp = __shfl_sync(0xffffffffu, tpl, j);
-          float x = __ldg(tb + (size_t)(tp & 0xffu) * ld) + __ldg(tb + (size_t)((tp >> 8) & 0xffu) * ld + ps);
-          if (c3) x += __ldg(tb + (size_t)((tp >> 16) & 0xffu) * ld + 2 * ps);
-          v[j] = x;
-        }
-      };
-      float run = 0.f;
+      uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
       for (int qp = 0; qp < nqp; ++qp, ++ke) {
         const int nw = min(2, nq - 2 * qp);
         for (int w = 0; w < 2; ++w) {
-          if (w >= nw) {
-            mbar_wait_wd(&bars[B_O_FULL + w], ke & 1);
-            mbar_arrive(&bars[B_O_EMPTY + w]);
-            continue;
-          }
-          const int q0 = (2 * qp + w) * 128;
-          float va[32], vb[32];
-          gather(q0, va);                                  // in flight while the last MMA2 of the tile completes
           mbar_wait_wd(&bars[B_O_FULL + w], ke & 1);
+          if (w >= nw) { mbar_arrive(&bars[B_O_EMPTY + w]); continue; }
           tc_fence_after();
-          auto chunk = [&](int ch, const float (&v)[32], float (&vn)[32]) {
-            uint32_t r[32];
+          const int q0 = (2 * qp + w) * 128;
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ch += 2) {
+            uint32_t r[32], r2[32];
             tmem_ld32(TM_O + lane_base + w * 128 + ch * 32, r);
-            if (ch < 3) gather(q0 + (ch + 1) * 32, vn);
+            tmem_ld32(TM_O + lane_base + w * 128 + ch * 32 + 32, r2);
             tmem_ld_wait();
-            if (ch == 3) { tc_fence_before(); mbar_arrive(&bars[B_O_EMPTY + w]); }
-            const int qc = q0 + ch * 32;
+            if (ch == 2) { tc_fence_before(); mbar_arrive(&bars[B_O_EMPTY + w]); }
             if (!head) {
-              float a0 = 0.f, a1 = 0.f;
 #pragma unroll
               for (int jj = 0; jj < 32; jj += 2) {
-                const float d0 = qc + jj < p.N ? v[jj] - __uint_as_float(r[jj]) : 0.f;
-                const float d1 = qc + jj + 1 < p.N ? v[jj + 1] - __uint_as_float(r[jj + 1]) : 0.f;
-                a0 = fmaf(d0, d0, a0);
-                a1 = fmaf(d1, d1, a1);
+                const uint64_t a = pack2u(r[jj], r[jj + 1]), b = pack2u(r2[jj], r2[jj + 1]);
+                acc2[(jj >> 1) & 1] = fma2(a, a, acc2[(jj >> 1) & 1]);
+                acc2[2 + ((jj >> 1) & 1)] = fma2(b, b, acc2[2 + ((jj >> 1) & 1)]);
               }
-              run += a0 + a1;
             } else if (d < p.L) {
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) {
-                const int q = qc + jj;
+              for (int jj = 0; jj < 64; ++jj) {
+                const int q = q0 + ch * 32 + jj;
                 if (q < p.N) {
-                  const float df = v[jj] - __uint_as_float(r[jj]);
+                  const float df = -__uint_as_float(jj < 32 ? r[jj & 31] : r2[jj & 31]);
                   const int col = q * p.L + d;
                   if (p.y_img) {
                     uint8_t *dst = reinterpret_cast<uint8_t *>(p.y_img) + ((size_t)(win >> 7) * p.y_nk + (col >> 6)) * (128 * 128);
@@ -479,14 +522,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_attn_tcn(const AttnNParams p) {
                 }
               }
             }
-          };
-          chunk(0, va, vb);
-          chunk(1, vb, va);
-          chunk(2, va, vb);
-          chunk(3, vb, va);
+          }
         }
       }
       if (!head) {
+        float al, ah;
+        unpack2(add2(add2(acc2[0], acc2[1]), add2(acc2[2], acc2[3])), al, ah);
+        float run = al + ah;
 #pragma unroll
         for (int o = 16; o; o >>= 1) run += __shfl_xor_sync(0xffffffffu, run, o);
         if (lane == 0) p.partial[(size_t)u * 4 + quad] = run;
@@ -620,6 +662,64 @@ __global__ void __launch_bounds__(128) k_prep_uc_tiles(const float *__restrict__
   }
 }
 
+// Selection operand A of one window: MINUS its per-frame table as hi + lo fp16 halves, K-major SW128 sub-tiles of 64 columns.
+// Column h*cT + p*T + t holds -(hi | lo)(tab[(win*T + t)*ld + off + p*pstride + row]); rows >= n_rows and columns >= 2cT are zero.
+// grid (n_win, nsel), 256 threads: thread = (row, 8-column chunk).
+__global__ void __launch_bounds__(256) k_prep_vq_img(const float *__restrict__ tab, int ld, int off, int pstride, int n_rows, int T, int c,
+                                                     int nsel, __half *__restrict__ img) {
+  const size_t win = blockIdx.x;
+  const int sub = blockIdx.y, cT = c * T;
+  uint8_t *out = reinterpret_cast<uint8_t *>(img) + (win * nsel + sub) * SUB_BYTES;
+  for (int e = threadIdx.x; e < 128 * 8; e += 256) {
+    const int row = e & 127, ch = e >> 7;             // consecutive threads -> consecutive rows (coalesced table reads)
+    uint32_t pk[4];
+#pragma unroll
+    for (int i2 = 0; i2 < 4; ++i2) {
+      float v[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int col = sub * 64 + ch * 8 + i2 * 2 + i;
+        const int hh = col / cT, pt = col - hh * cT;
+        float x = 0.f;
+        if (hh < 2 && row < n_rows) {
+          const int pp = pt / T, t = pt - pp * T;
+          const float f = -__ldg(tab + (win * T + t) * (size_t)ld + off + pp * pstride + row);
+          const float hi = __half2float(__float2half_rn(f));
+          x = hh == 0 ? hi : f - hi;
+        }
+        v[i] = x;
+      }
+      pk[i2] = pack_half2(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4 *>(out + sw128_offset(row, ch * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// Selection operand B of one query tile: Sel[q][h*cT + p*T + frame_p(q)] = 1 for both halves h, rows of pad tuples are zero.
+// grid (nq, nsel), 256 threads.
+__global__ void __launch_bounds__(256) k_prep_sel_tiles(const uint32_t *__restrict__ tup, int N, int T, int c, int nsel, __half *__restrict__ img) {
+  const int qt = blockIdx.x, sub = blockIdx.y, cT = c * T;
+  uint8_t *out = reinterpret_cast<uint8_t *>(img) + ((size_t)qt * nsel + sub) * SUB_BYTES;
+  for (int e = threadIdx.x; e < 128 * 8; e += 256) {
+    const int row = e >> 3, ch = e & 7, q = qt * 128 + row;
+    const uint32_t tp = q < N ? tup[q] : 0u;
+    uint32_t pk[4];
+#pragma unroll
+    for (int i2 = 0; i2 < 4; ++i2) {
+      float v[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int col = sub * 64 + ch * 8 + i2 * 2 + i;
+        const int hh = col / cT, pt = col - hh * cT;
+        const int pp = pt / T, t = pt - pp * T;
+        v[i] = (q < N && hh < 2 && (int)((tp >> (8 * pp)) & 0xffu) == t) ? 1.f : 0.f;
+      }
+      pk[i2] = pack_half2(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4 *>(out + sw128_offset(row, ch * 8)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 // Head table: UAB[row][p*32 + l] = sum_d Wdr[l][d] . Gv_p[row][d] (+ bdr[l] for p == 0); rows = n_win*T, pair tuples
 __global__ void __launch_bounds__(128) k_head_uab(const float *__restrict__ G, int ldg, int voff, const float *__restrict__ dr_w,
                                                   const float *__restrict__ dr_b, float *__restrict__ uab, int64_t rows, int L) {
@@ -682,6 +782,10 @@ int arx_tcn_prep_support(arx_handle *h, ArxTransformer &tr, int way, bool with_h
     ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.tup_packed), (size_t)tr.N * sizeof(uint32_t)));
     k_pack_tuples<<<(tr.N + 127) / 128, 128, 0, st>>>(tr.tuples, tr.tup_packed, tr.N, tr.c);
     ARX_LAUNCH_CHECK(h);
+    const int nsel = (2 * tr.c * h->T + 63) / 64;
+    ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tr.sel_tiles), (size_t)ns * nsel * SUB_BYTES));
+    k_prep_sel_tiles<<<dim3(ns, nsel), 256, 0, st>>>(tr.tup_packed, tr.N, h->T, tr.c, nsel, tr.sel_tiles);
+    ARX_LAUNCH_CHECK(h);
   }
   k_prep_kc_tiles<<<dim3(way, ns), 256, 0, st>>>(tr.ks, tr.kc_tiles, tr.N, ns);
   ARX_LAUNCH_CHECK(h);
@@ -720,6 +824,8 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
     h->zscratch_bytes = zbytes;
   }
   p.zscratch = h->zscratch + (p.mode == 1 ? zhalf : 0);
+  p.trace = h->trace_buf;
+  p.free_a = h->tcn_free_a;
   p.poly = (h->tcn_poly && p.ns >= 8) ? 1 : 0;      // measured on B200: +3.4 % at N=4960 (MUFU-bound pass), -5 % at N=496 (latency-bound)
   if (!h->tcn_diag) {
     ARX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&h->tcn_diag), 8 * sizeof(int)));
@@ -746,24 +852,38 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
   return ARX_OK;
 }
 
+static int tcn_nsel(const arx_handle *h, const ArxTransformer &tr) { return (2 * tr.c * h->T + 63) / 64; }
+
+// selection operand A (minus the per-frame table, hi | lo) of n_win windows from a row-major table
+static int tcn_prep_vq(arx_handle *h, const ArxTransformer &tr, const float *tab, int ld, int off, int pstride, int n_rows, int64_t n_win,
+                       __half *vq, cudaStream_t st) {
+  const int nsel = tcn_nsel(h, tr);
+  for (int64_t b0 = 0; b0 < n_win; b0 += 32768) {
+    const int64_t nb = std::min<int64_t>(32768, n_win - b0);
+    k_prep_vq_img<<<dim3((unsigned)nb, nsel), 256, 0, st>>>(tab + (size_t)b0 * h->T * ld, ld, off, pstride, n_rows, h->T, tr.c, nsel,
+                                                            vq + (size_t)b0 * nsel * 8192);
+    ARX_LAUNCH_CHECK(h);
+  }
+  return ARX_OK;
+}
+
 // squared-distance partials only (the streaming tail forms logits / argmax itself)
 int arx_tcn_attention_partial(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
-                              float *partial, cudaStream_t st) {
+                              float *partial, __half *vq_ws, cudaStream_t st) {
+  int rc = tcn_prep_vq(h, tr, G, ldg, tr.c * h->D, h->D, 128, n_win, vq_ws, st);
+  if (rc) return rc;
   AttnNParams p{};
-  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.vct_tiles; p.tab = G; p.tup = tr.tup_packed; p.partial = partial;
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.vct_tiles; p.vq_img = vq_ws; p.sel_img = tr.sel_tiles; p.nsel = tcn_nsel(h, tr);
+  p.partial = partial;
   p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
-  p.tab_ld = ldg; p.tab_off = tr.c * h->D; p.tab_pstride = h->D; p.mode = 0;
+  p.mode = 0;
   return tcn_launch(h, tr, p, (int)n_win * way, st);
 }
 
 // logits (n_win, way) and chosen (n_win) of transformer `tr` from the query tiles; G = row-major per-frame projections
 int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, int way,
-                      float *partial, float *logits, int32_t *chosen, cudaStream_t st) {
-  AttnNParams p{};
-  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.vct_tiles; p.tab = G; p.tup = tr.tup_packed; p.partial = partial;
-  p.n_win = (int)n_win; p.way = way; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
-  p.tab_ld = ldg; p.tab_off = tr.c * h->D; p.tab_pstride = h->D; p.mode = 0;
-  int rc = tcn_launch(h, tr, p, (int)n_win * way, st);
+                      float *partial, float *logits, int32_t *chosen, __half *vq_ws, cudaStream_t st) {
+  int rc = arx_tcn_attention_partial(h, tr, kq_tiles, G, ldg, n_win, way, partial, vq_ws, st);
   if (rc) return rc;
   k_finish_n<<<(unsigned)((n_win + 127) / 128), 128, 0, st>>>(partial, logits, chosen, n_win, way, tr.N);
   ARX_LAUNCH_CHECK(h);
@@ -773,28 +893,34 @@ int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_
 // streaming: the head input of EVERY class of ONE window at once (y_all (way, N*L) fp32), so that it can run beside the main
 // attention launch instead of after it; `iota` = device array 0..way-1
 int arx_tcn_head_all(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int way, const int32_t *iota,
-                     float *uab, float *y_all, cudaStream_t st) {
+                     float *uab, float *y_all, __half *vq_ws, cudaStream_t st) {
   if (tr.c != 2 || h->T > 32 || !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "tcn_head: pair tuples with T <= 32 only");
   k_head_uab<<<(unsigned)h->T, 128, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, h->T, h->T);
   ARX_LAUNCH_CHECK(h);
+  int rc = tcn_prep_vq(h, tr, uab, 64, 0, 32, h->T, 1, vq_ws, st);
+  if (rc) return rc;
   AttnNParams p{};
-  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.uc_tiles; p.tab = uab; p.tup = tr.tup_packed; p.chosen = iota;
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.uc_tiles; p.vq_img = vq_ws; p.sel_img = tr.sel_tiles; p.nsel = tcn_nsel(h, tr);
+  p.chosen = iota;
   p.y = y_all; p.y_img = nullptr; p.y_nk = 0; p.L = h->T;
   p.n_win = way; p.way = 1; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
-  p.tab_ld = 64; p.tab_off = 0; p.tab_pstride = 32; p.mode = 1; p.same_window = 1;
+  p.mode = 1; p.same_window = 1;
   return tcn_launch(h, tr, p, way, st);
 }
 
 // open-set head input y = dimensionality_reduction(diff of the winning class) (model.py:323-324,196), pair tuples
 int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
-                 float *uab, float *y, __half *y_img, int y_nk, cudaStream_t st) {
+                 float *uab, float *y, __half *y_img, int y_nk, __half *vq_ws, cudaStream_t st) {
   if (tr.c != 2 || h->T > 32 || !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "tcn_head: pair tuples with T <= 32 only");
   k_head_uab<<<(unsigned)(n_win * h->T), 128, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, n_win * h->T, h->T);
   ARX_LAUNCH_CHECK(h);
+  int rc = tcn_prep_vq(h, tr, uab, 64, 0, 32, h->T, n_win, vq_ws, st);
+  if (rc) return rc;
   AttnNParams p{};
-  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.uc_tiles; p.tab = uab; p.tup = tr.tup_packed; p.chosen = chosen;
+  p.kq_img = kq_tiles; p.kc_img = tr.kc_tiles; p.vct_img = tr.uc_tiles; p.vq_img = vq_ws; p.sel_img = tr.sel_tiles; p.nsel = tcn_nsel(h, tr);
+  p.chosen = chosen;
   p.y = y; p.y_img = y_img; p.y_nk = y_nk; p.L = h->T;
   p.n_win = (int)n_win; p.way = 1; p.N = tr.N; p.T = h->T; p.c = tr.c; p.nq = p.ns = tr.Npad / 128;
-  p.tab_ld = 64; p.tab_off = 0; p.tab_pstride = 32; p.mode = 1;
+  p.mode = 1;
   return tcn_launch(h, tr, p, (int)n_win, st);
 }

@@ -12,10 +12,11 @@ support, labels, query, _ = make_episode(cfg, B, 71, "structured")
 m.set_support(poses=torch.from_numpy(support[0]).cuda()); Q = torch.from_numpy(query).cuda()
 qf = m.embed(Q[:37])
 lo, it = TrxOracle(cfg, sd).score(support, labels, query[:16], chunk=16)
-for poly in (0, 1, 0, 1):
+for poly, free in ((0, 0), (1, 0), (0, 1), (1, 1)):
     m.debug_set(6, poly)
+    m.debug_set(7, free)
     ms_p = timed(lambda: m.score(Q), 3)
     ms_t = timed(lambda: m.score_features(1, qf), 2)
     lg, t = m.score(Q[:16])
-    print(f"poly={poly}: pairs {B / ms_p * 1e3:.0f} windows/s ({ms_p:.2f} ms), triples {37 / ms_t * 1e3:.0f} windows/s ({ms_t:.2f} ms), "
+    print(f"poly={poly} free_a={free}: pairs {B / ms_p * 1e3:.0f} windows/s ({ms_p:.2f} ms), triples {37 / ms_t * 1e3:.0f} windows/s ({ms_t:.2f} ms), "
           f"logit err {rel_err(lg.cpu(), lo).max():.2e}", flush=True)
