@@ -347,6 +347,12 @@ int arx_load_weights(arx_handle *h, const arx_weights *w, void *stream) {
     }
     h->tc_linears = true;
   }
+  h->mlp_bias_host_ok = false;
+  if (h->tc_linears && h->tl_fc1.BN == 192 && h->tl_fc1.n_tiles == 1 && h->tl_fc2.BN == 256 && h->tl_fc2.n_tiles == 1) {
+    ARX_CUDA(h, cudaMemcpyAsync(h->mlp_bias_host, h->tl_fc1.bias, 192 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ARX_CUDA(h, cudaMemcpyAsync(h->mlp_bias_host + 192, h->tl_fc2.bias, 256 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    h->mlp_bias_host_ok = true;
+  }
   ARX_CUDA(h, cudaStreamSynchronize(st));
   h->weights_loaded = true;
   h->weights_gen++;
@@ -947,8 +953,13 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
         return ARX_OK;
       }
       if (from_frames) {
-        if ((rc = arx_tc_rows_to_img(h, query_dev + b0 * h->T * h->J3, h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
-        if (p_embed) {
+        // (an fp16 pass -- arx_score_host*_f16 -- carries its rows at half the stride)
+        const void *xq = h->query_f16 ? static_cast<const void *>(reinterpret_cast<const __half *>(query_dev) + b0 * h->T * h->J3)
+                                      : static_cast<const void *>(query_dev + b0 * h->T * h->J3);
+        if (p_embed && (h->tc_variant & 8192) == 0 && arx_mlp_fused_supported(h, xq)) {
+          if ((rc = arx_mlp_fused(h, xq, h->query_f16, rows, w.f_img, f_nk, f_onehot, st))) return rc;      // one launch: poses -> feature image
+        } else if ((rc = arx_tc_rows_to_img(h, static_cast<const float *>(xq), h->J3, h->J3, rows, w.x_img, h->tl_fc1.nk, -1, st))) return rc;
+        else if (p_embed) {
           if ((rc = arx_tcp_linear_img(h, h->tl_fc1, w.x_img, rows, ARX_ACT_RELU, w.h_img, h->tl_fc2.nk, -1, st))) return rc;
           if ((rc = arx_tcp_linear_img(h, h->tl_fc2, w.h_img, rows, ARX_ACT_RELU, w.f_img, f_nk, f_onehot, st))) return rc;
         } else {
@@ -1553,6 +1564,7 @@ int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
       cudaFree(h->trace_buf);
       h->trace_buf = nullptr;
     }
+    h->trace_sel = value;        // 1: attention kernels, 2: fused frame MLP
     return ARX_OK;
   }
   return arx_fail(h, ARX_ERR_INVALID, "debug_set: unknown key %d", key);

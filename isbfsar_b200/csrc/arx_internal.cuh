@@ -164,10 +164,13 @@ struct arx_handle {
   size_t zscratch_bytes = 0;
   ArxStream stream;
   uint64_t tiles_gen[ARX_MAX_TRANSFORMERS] = {0, 0, 0, 0};   // support generation the tiled operands were built for (+1)
+  float mlp_bias_host[192 + 256] = {};   // host copies of the (zero padded) fc1 / fc2 biases: kernel-parameter operands of k_mlp_p
+  bool mlp_bias_host_ok = false;
   int tcn_free_a = 1;               // tiled attention, pass A: softmax groups free-running (debug key 7)
   int tcn_poly = 1;                 // tiled attention, pass A: half of the exponentials on the FMA pipe (debug key 6)
   int *tcn_diag = nullptr;          // watchdog record of the tiled attention kernel
   long long *trace_buf = nullptr;   // debug: device buffer for kernel timeline traces (arx_debug_set key 1)
+  int trace_sel = 0;                // which kernel writes it: 1 attention kernels, 2 fused frame MLP
   int attn_stagger = -1;     // k_attn_tc3 softmax groups: < 0 = take turns on the MUFU phase (token), >= 0 = free-running, group 1 this many clocks behind (debug key 3)
   int attn_poly = 0;         // k_attn_tc3: every attn_poly-th register pair takes the FMA-pipe exp2 polynomial (0 = none; debug key 4)
   bool pdl = false;     // programmatic dependent launch for the arx_score kernel chain (debug key 2; measured: no gain, off by default)
@@ -282,6 +285,9 @@ int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
                              float *partial, int g_ld, int g_voff, bool g_chunked, bool episodes, cudaStream_t st);
 // ---- persistent GEMM + tuple images (arx_gemm_p.cu)
 bool arx_tcp_supported(const ArxTcLinear &L);
+// fused frame MLP (arx_mlp_p.cu)
+bool arx_mlp_fused_supported(const arx_handle *h, const void *x);
+int arx_mlp_fused(arx_handle *h, const void *x, bool f16, int64_t rows, __half *f_img, int c_nk, int onehot_sub, cudaStream_t st);
 int arx_tcp_linear_img(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int64_t M, int act, __half *c_img, int c_nk, int onehot_sub,
                        cudaStream_t st);
 int arx_tcp_linear_chunked(arx_handle *h, const ArxTcLinear &L, const __half *a_img, int a_nk, int64_t M, float *gc, cudaStream_t st);

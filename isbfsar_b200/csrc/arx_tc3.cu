@@ -387,7 +387,7 @@ int arx_tc3_attention_launch(arx_handle *h, const ArxTransformer &tr, const __ha
                              float *partial, int g_ld, int g_voff, bool g_chunked, bool episodes, cudaStream_t st) {
   Attn3Params p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.vct_img = tr.vs_img_bf; p.G = G; p.partial = partial;
-  p.n_win = (int)n_win; p.way = way; p.ldg = g_ld; p.voff = g_voff; p.trace = h->trace_buf;
+  p.n_win = (int)n_win; p.way = way; p.ldg = g_ld; p.voff = g_voff; p.trace = h->trace_sel == 1 ? h->trace_buf : nullptr;
   p.gchunk = g_chunked ? 1 : 0;
   p.ep = episodes ? 1 : 0;
   p.token = h->attn_stagger < 0;

@@ -824,7 +824,7 @@ static int tcn_launch(arx_handle *h, const ArxTransformer &tr, AttnNParams &p, i
     h->zscratch_bytes = zbytes;
   }
   p.zscratch = h->zscratch + (p.mode == 1 ? zhalf : 0);
-  p.trace = h->trace_buf;
+  p.trace = h->trace_sel == 1 ? h->trace_buf : nullptr;
   p.free_a = h->tcn_free_a;
   p.poly = (h->tcn_poly && p.ns >= 8) ? 1 : 0;      // measured on B200: +3.4 % at N=4960 (MUFU-bound pass), -5 % at N=496 (latency-bound)
   if (!h->tcn_diag) {

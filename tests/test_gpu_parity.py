@@ -419,6 +419,43 @@ def test_persistent_gemm_path_large_batch():
     assert rel_err(a_lo[-64:].cpu(), lo).max() < TOL_TC and rel_err(a_it[-64:].cpu(), it).max() < TOL_TC
 
 
+def test_fused_frame_mlp_is_bit_identical():
+    """Big batches embed the frames with ONE fused kernel (poses -> fc1 -> fc2 -> feature image, arx_mlp_p.cu); variant 8192 keeps
+    the three launches it replaces.  Same operands, same rounding: the scores must agree bit for bit -- fp32 rows on the device,
+    fp32 and fp16 rows through the host-buffer entry points (ragged last row tile)."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    n = 2 * 148 * 8 + 13
+    support, labels, query, _ = make_episode(cfg, n, 95, "structured")
+    m.set_support(poses=torch.from_numpy(support[0]).cuda())
+    Q = torch.from_numpy(query).cuda()
+    a_lo, a_it = m.score(Q)
+    launches = m.launch_count()
+    m.score(Q)
+    fused_launches = m.launch_count() - launches
+    m.debug_set(0, 8192)
+    b_lo, b_it = m.score(Q)
+    launches = m.launch_count()
+    m.score(Q)
+    assert m.launch_count() - launches == fused_launches + 2          # pose image + fc1 + fc2 instead of one launch
+    assert torch.equal(a_lo, b_lo) and torch.equal(a_it, b_it)
+    lo, it = TrxOracle(cfg, sd).score(support, labels, query[-64:])
+    assert rel_err(a_lo[-64:].cpu(), lo).max() < TOL_TC and rel_err(a_it[-64:].cpu(), it).max() < TOL_TC
+    # host rows: two chunks of >= 2 tiles per SM each, fp32 and fp16
+    nb = 2 * (2 * 148 * 8 + 40)
+    support, labels, query, _ = make_episode(cfg, nb, 96, "structured")
+    q16 = torch.from_numpy(query).to(torch.float16)
+    q32 = q16.to(torch.float32)
+    res = {}
+    for bits in (0, 8192):
+        m.debug_set(0, bits)
+        res[bits] = (m.score_host(q32.pin_memory()), m.score_host(q16.pin_memory()))
+    m.debug_set(0, 0)
+    for k in range(2):
+        assert torch.equal(res[0][0][k], res[8192][0][k]) and torch.equal(res[0][1][k], res[8192][1][k])
+        assert torch.equal(res[0][0][k], res[0][1][k])
+
+
 def test_streaming_host_api_matches_device_path():
     """arx_score_host_submit/_wait: several requests in flight, interleaved with blocking and device-side calls and a
     support-set change; every result equals the device path bit for bit."""
