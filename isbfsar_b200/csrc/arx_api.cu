@@ -1564,7 +1564,7 @@ int arx_debug_set(arx_handle *h, int32_t key, int32_t value) {
       cudaFree(h->trace_buf);
       h->trace_buf = nullptr;
     }
-    h->trace_sel = value;        // 1: attention kernels, 2: fused frame MLP
+    h->trace_sel = value;        // 1: attention kernels, 2: fused frame MLP, 3: head kernel
     return ARX_OK;
   }
   return arx_fail(h, ARX_ERR_INVALID, "debug_set: unknown key %d", key);

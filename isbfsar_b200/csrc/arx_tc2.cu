@@ -60,11 +60,12 @@ namespace {
 constexpr uint32_t H2_OFF_KQ = 0;                       // 2 x 32 KB
 constexpr uint32_t H2_OFF_KC = 2 * IMG_BYTES;           // 2 x 32 KB
 constexpr uint32_t H2_OFF_P = 4 * IMG_BYTES;            // 2 x 32 KB (one per softmax group)
-constexpr uint32_t H2_OFF_UC = 6 * IMG_BYTES;           // 2 x 4 KB
+constexpr uint32_t H2_OFF_UC = 6 * IMG_BYTES;           // NUC x 4 KB
+constexpr int NUC = 4;                                  // Uc ring: deeper than the Kq/Kc ring, see the producer
 constexpr uint32_t UC_BYTES = 16 * DD * 2;
-constexpr uint32_t H2_OFF_BAR = 6 * IMG_BYTES + 2 * UC_BYTES;
-enum { H2_FULL_KK = 0, H2_EMPTY_KK = 2, H2_FULL_UC = 4, H2_EMPTY_UC = 6, H2_S_FULL = 8, H2_S_EMPTY = 10, H2_P_FULL = 12, H2_P_EMPTY = 14,
-       H2_Y_FULL = 16, H2_Y_EMPTY = 18, H2_COUNT = 20 };
+constexpr uint32_t H2_OFF_BAR = 6 * IMG_BYTES + NUC * UC_BYTES;
+enum { H2_FULL_KK = 0, H2_EMPTY_KK = 2, H2_S_FULL = 4, H2_S_EMPTY = 6, H2_P_FULL = 8, H2_P_EMPTY = 10, H2_Y_FULL = 12, H2_Y_EMPTY = 14,
+       H2_FULL_UC = 16, H2_EMPTY_UC = 16 + NUC, H2_COUNT = 16 + 2 * NUC };
 constexpr uint32_t H2_SMEM_BYTES = H2_OFF_BAR + H2_COUNT * 8 + 16 + 1024;
 
 struct Head2Params {
@@ -73,11 +74,15 @@ struct Head2Params {
   const int32_t *chosen;
   __half *y_img;           // fp16 activation image [ceil(n_win/128)][y_nk][128 x 64]
   int n_win, y_nk;
+  long long *trace;        // optional timeline of CTA 0 (bring-up): [3 roles: producer, softmax group 0, epilogue][64 windows][8 stamps]
+  int l2_ahead;            // producer: L2 prefetch distance in windows of this CTA (huge = off)
   int cls_stride;          // episode mode: window b's classes start at b*cls_stride (0: one support set for all windows)
 };
 
 // per slot of the padded-triangular order: i | j << 8 | (lexicographic rank + 1) << 16 (0 = pad)
 __constant__ uint32_t c_slot_info[128];
+
+#define HTRACE(role, step, slot) do { if (p.trace && blockIdx.x == 0 && (step) < 64) p.trace[(((role) * 64) + (step)) * 8 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -89,11 +94,11 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[H2_FULL_KK + i], 1); mbar_init(&bars[H2_EMPTY_KK + i], 1);
-      mbar_init(&bars[H2_FULL_UC + i], 1); mbar_init(&bars[H2_EMPTY_UC + i], 1);
       mbar_init(&bars[H2_S_FULL + i], 1); mbar_init(&bars[H2_S_EMPTY + i], 128);
       mbar_init(&bars[H2_P_FULL + i], 128); mbar_init(&bars[H2_P_EMPTY + i], 1);
       mbar_init(&bars[H2_Y_FULL + i], 1); mbar_init(&bars[H2_Y_EMPTY + i], 128);
     }
+    for (int i = 0; i < NUC; ++i) { mbar_init(&bars[H2_FULL_UC + i], 1); mbar_init(&bars[H2_EMPTY_UC + i], 1); }
     mbar_init_fence();
   }
   pdl_trigger();
@@ -109,20 +114,39 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
     setmaxnreg_dec<40>();
     if (warp == 0) {
       if (elect_one()) {            // producer: {Kq[b], Kc[c*]} then Uc[c*] per tile, two stages
+        for (int f = 1; f < p.l2_ahead && f < ntiles; ++f)
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)(blockIdx.x + f * gridDim.x) * IMG_BYTES, IMG_BYTES);
+        // the class of the NEXT window is fetched while this window's copies are issued: a dependent load of `chosen` at the top
+        // of every iteration put an L2 round trip on the producer's critical path
+        int c_next = ntiles ? p.chosen[blockIdx.x] + (int)blockIdx.x * p.cls_stride : 0;
         for (int f = 0; f < ntiles; ++f) {
-          const int b = blockIdx.x + f * gridDim.x, c = p.chosen[b] + b * p.cls_stride, st = f & 1;
+          const int b = blockIdx.x + f * gridDim.x, c = c_next, st = f & 1;
+          if (f + 1 < ntiles) c_next = p.chosen[b + gridDim.x] + (b + (int)gridDim.x) * p.cls_stride;
           const uint8_t *kq = reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)b * IMG_BYTES;
           const uint8_t *kc = reinterpret_cast<const uint8_t *>(p.kc_img) + (size_t)c * IMG_BYTES;
+          // the ring is two windows deep and a Kq image comes from HBM (the attention kernel read 134 MB since): with the DRAM
+          // latency under load (~5 K clk) on every stage the kernel ran at ~3.1 K clk per window.  Pull the images of the windows
+          // a few stages ahead into L2 now, so that the ring only sees the L2 latency.
+          HTRACE(0, f, 0);
+          if (f + p.l2_ahead < ntiles)
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t *>(p.kq_img) + (size_t)(b + p.l2_ahead * gridDim.x) * IMG_BYTES, IMG_BYTES);
           mbar_wait(&bars[H2_EMPTY_KK + st], ((f >> 1) & 1) ^ 1);
+          HTRACE(0, f, 1);
           mbar_arrive_expect_tx(&bars[H2_FULL_KK + st], 2 * IMG_BYTES);
           bulk_g2s(smem + H2_OFF_KQ + st * IMG_BYTES, kq, SUB_BYTES, &bars[H2_FULL_KK + st]);
           bulk_g2s(smem + H2_OFF_KQ + st * IMG_BYTES + SUB_BYTES, kq + SUB_BYTES, SUB_BYTES, &bars[H2_FULL_KK + st]);
           bulk_g2s(smem + H2_OFF_KC + st * IMG_BYTES, kc, SUB_BYTES, &bars[H2_FULL_KK + st]);
           bulk_g2s(smem + H2_OFF_KC + st * IMG_BYTES + SUB_BYTES, kc + SUB_BYTES, SUB_BYTES, &bars[H2_FULL_KK + st]);
-          mbar_wait(&bars[H2_EMPTY_UC + st], ((f >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[H2_FULL_UC + st], UC_BYTES);
-          bulk_g2s(smem + H2_OFF_UC + st * UC_BYTES, reinterpret_cast<const uint8_t *>(p.uc_img) + (size_t)c * UC_BYTES, UC_BYTES,
-                   &bars[H2_FULL_UC + st]);
+          HTRACE(0, f, 2);
+          // A Uc stage is released by the Y MMA at the very END of a window's pipeline, a Kq/Kc stage by MMA1 at its start: with
+          // two Uc stages this wait held back the NEXT window's Kq/Kc copies and exposed their latency on every other window
+          // (timeline trace, tools/trace_head.py: 2.6 K clk per window).  Four 4 KB stages: the wait is always long satisfied.
+          const int su = f % NUC;
+          mbar_wait(&bars[H2_EMPTY_UC + su], ((f / NUC) & 1) ^ 1);
+          HTRACE(0, f, 3);
+          mbar_arrive_expect_tx(&bars[H2_FULL_UC + su], UC_BYTES);
+          bulk_g2s(smem + H2_OFF_UC + su * UC_BYTES, reinterpret_cast<const uint8_t *>(p.uc_img) + (size_t)c * UC_BYTES, UC_BYTES,
+                   &bars[H2_FULL_UC + su]);
         }
       }
     } else if (warp == 1) {
@@ -132,9 +156,12 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
         const uint32_t sbase = smem_u32(smem);
         for (int f = 0; f < ntiles; ++f) {
           const int st = f & 1;
+          HTRACE(0, f, 4);
           mbar_wait(&bars[H2_FULL_KK + st], (f >> 1) & 1);
+          HTRACE(0, f, 5);
           mbar_wait(&bars[H2_S_EMPTY + st], ((f >> 1) & 1) ^ 1);
           tc_fence_after();
+          HTRACE(0, f, 6);
           const uint32_t a0 = sbase + H2_OFF_KC + st * IMG_BYTES, b0 = sbase + H2_OFF_KQ + st * IMG_BYTES;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
@@ -153,7 +180,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
         const uint32_t sbase = smem_u32(smem);
         for (int f = 0; f < ntiles; ++f) {
           const int st = f & 1;
-          mbar_wait(&bars[H2_FULL_UC + st], (f >> 1) & 1);
+          const int su = f % NUC;
+          mbar_wait(&bars[H2_FULL_UC + su], (f / NUC) & 1);
           mbar_wait(&bars[H2_P_FULL + st], (f >> 1) & 1);
           mbar_wait(&bars[H2_Y_EMPTY + st], ((f >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -161,11 +189,11 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
           for (int kk = 0; kk < 8; ++kk) {
             const uint32_t boff = (kk >> 2) * (16 * 128) + (kk & 3) * 32;
             mma_f16_ss(TM_Y + st * 32, smem_desc_at(DESC_MN, sbase + H2_OFF_P + st * IMG_BYTES + kk * 2048),
-                       smem_desc_at(DESC_K, sbase + H2_OFF_UC + st * UC_BYTES + boff), IDESCY, kk > 0);
+                       smem_desc_at(DESC_K, sbase + H2_OFF_UC + su * UC_BYTES + boff), IDESCY, kk > 0);
           }
           mma_commit(&bars[H2_Y_FULL + st]);
           mma_commit(&bars[H2_P_EMPTY + st]);
-          mma_commit(&bars[H2_EMPTY_UC + st]);
+          mma_commit(&bars[H2_EMPTY_UC + su]);
         }
       }
     }
@@ -175,9 +203,12 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
     const int s = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint8_t *prow = smem + H2_OFF_P + g * IMG_BYTES + (s >> 3) * 1024 + (s & 7) * 128;
+    const bool trc = (threadIdx.x & 127) == 0;
     for (int f = g; f < ntiles; f += 2) {
+      if (trc) HTRACE(1, f, 0);
       mbar_wait(&bars[H2_S_FULL + g], (f >> 1) & 1);
       tc_fence_after();
+      if (trc) HTRACE(1, f, 1);
       uint32_t r[128];
       tmem_ld32(TM_S + lane_base + g * 128 + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
       tmem_ld32(TM_S + lane_base + g * 128 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
@@ -186,8 +217,10 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bars[H2_S_EMPTY + g]);
+      if (trc) HTRACE(1, f, 2);
 #pragma unroll
       for (int j = 0; j < 128; ++j) r[j] = ex2_bits(r[j]);
+      if (trc) HTRACE(1, f, 3);
       zero_pads(r, std::make_integer_sequence<int, 8>{});
       uint64_t z0 = 0ull, z1 = 0ull;
 #pragma unroll
@@ -199,7 +232,9 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
       unpack2(add2(z0, z1), zl, zh);
       const float zinv = __frcp_rn(zl + zh);
       const uint64_t zz = pack2(zinv, zinv);
+      if (trc) HTRACE(1, f, 4);
       mbar_wait(&bars[H2_P_EMPTY + g], ((f >> 1) & 1) ^ 1);
+      if (trc) HTRACE(1, f, 5);
 #pragma unroll
       for (int c16 = 0; c16 < 16; ++c16) {
         uint32_t h[4];
@@ -213,6 +248,7 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
       }
       fence_proxy_async_smem();
       mbar_arrive(&bars[H2_P_FULL + g]);
+      if (trc) HTRACE(1, f, 6);
     }
   } else {
     // ---------------- epilogue warps: thread == query-tuple slot q == TMEM lane of Y
@@ -221,17 +257,24 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t info = c_slot_info[q];
     const int fi = info & 0xff, fj = (info >> 8) & 0xff, rank = (int)(info >> 16) - 1;
+    // the head-table rows of the NEXT window are fetched while this one is finished: loaded at the top of their own iteration
+    // their L2 latency sat between the Y accumulator and the stores, ~1.9 K clk per window (timeline trace) -- the epilogue,
+    // not the softmax groups, paced the kernel
+    float4 ua[4], ub[4], na[4], nb[4];
+    auto load_u = [&](int b, float4 (&a)[4], float4 (&bb)[4]) {
+      const float4 *pa = reinterpret_cast<const float4 *>(p.uab + ((size_t)b * 16 + fi) * 32);
+      const float4 *pb = reinterpret_cast<const float4 *>(p.uab + ((size_t)b * 16 + fj) * 32 + 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = __ldg(pa + k); bb[k] = __ldg(pb + k); }
+    };
+    if (rank >= 0 && ntiles > 0) load_u(blockIdx.x, ua, ub);
     for (int f = 0; f < ntiles; ++f) {
       const int b = blockIdx.x + f * gridDim.x, st = f & 1;
-      float4 ua[4], ub[4];
-      if (rank >= 0) {
-        const float4 *pa = reinterpret_cast<const float4 *>(p.uab + ((size_t)b * 16 + fi) * 32);
-        const float4 *pb = reinterpret_cast<const float4 *>(p.uab + ((size_t)b * 16 + fj) * 32 + 16);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { ua[k] = __ldg(pa + k); ub[k] = __ldg(pb + k); }
-      }
+      if (rank >= 0 && f + 1 < ntiles) load_u(b + gridDim.x, na, nb);
+      if (q == 0) HTRACE(2, f, 0);
       mbar_wait(&bars[H2_Y_FULL + st], (f >> 1) & 1);
       tc_fence_after();
+      if (q == 0) HTRACE(2, f, 1);
       uint32_t yv[16];
       tmem_ld16(TM_Y + lane_base + st * 32, yv);
       tmem_ld_wait();
@@ -256,6 +299,8 @@ __global__ void __launch_bounds__(NTHREADS2, 1) k_head2_tc(const Head2Params p) 
           *reinterpret_cast<uint4 *>(dst + sw128_offset(b & 127, (col & 63) + l)) = pk;
         }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { ua[k] = na[k]; ub[k] = nb[k]; }
     }
   }
   tc_fence_before();
@@ -340,6 +385,8 @@ int arx_tc2_head_launch(arx_handle *h, const ArxTransformer &tr, const __half *k
                         __half *y_img, int y_nk, int cls_stride, cudaStream_t st) {
   Head2Params p{};
   p.kq_img = kq_img; p.kc_img = tr.ks_img; p.uc_img = tr.uc_img; p.uab = uab; p.chosen = chosen; p.y_img = y_img; p.n_win = (int)n_win; p.y_nk = y_nk; p.cls_stride = cls_stride;
+  p.l2_ahead = (h->tc_variant & 16384) ? 1 << 30 : 4;
+  p.trace = h->trace_sel == 3 ? h->trace_buf : nullptr;
   const int grid = n_win < h->sm_count ? (int)n_win : h->sm_count;
   { const int rc_ = arx_func_smem(h, k_head2_tc, (int)H2_SMEM_BYTES); if (rc_) return rc_; }
   ARX_CUDA(h, arx_launch_pdl(k_head2_tc, dim3(grid), dim3(NTHREADS2), H2_SMEM_BYTES, st, h->pdl, p));

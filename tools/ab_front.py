@@ -1,4 +1,5 @@
-"""A/B of the front-end variants of the cfg2 step on the GPU box (debug key 0 bits): fused frame MLP (8192 = off).
+"""A/B of variants of the cfg2 step on the GPU box (debug key 0 bits): fused frame MLP (8192 = off), L2 prefetch ahead of the
+head kernel's operand ring (16384 = off).
 Every variant: whole arx_score of 4096 windows timed with CUDA events, L2 flushed before every call; bit-equality of
 the scores against the default variant; then the per-stage timers of an eager pass."""
 import os, sys
@@ -30,7 +31,7 @@ def timed(reps=30):
 
 
 ref = None
-for name, bits in (("default", 0), ("mlp unfused", 8192)):
+for name, bits in (("default", 0), ("mlp unfused", 8192), ("no L2 prefetch in the head kernel", 16384), ("both off (round-2 mid state)", 8192 | 16384)):
     m.debug_set(0, bits)
     ms = timed()
     lg, t = res[0].clone(), res[1].clone()
