@@ -184,6 +184,8 @@ int arx_create(const arx_config *cfg, arx_handle **out) {
   h->cfg = *cfg;
   h->device = dev;
   h->sm_count = prop.multiProcessorCount;
+  if (const char *e = getenv("ARX_SM_RESERVE")) h->sm_reserve_n = std::max(0, std::min(atoi(e), h->sm_count / 2));
+  if (const char *e = getenv("ARX_VARIANT")) h->tc_variant = atoi(e);      // bring-up: initial value of debug key 0 (A/B runs of bench.py)
   h->T = cfg->seq_len;
   h->J3 = cfg->n_joints * 3;
   h->H = cfg->n_joints * 6;
@@ -436,10 +438,12 @@ static int support_fork(arx_handle *h, cudaStream_t st, cudaStream_t *side) {
 static int support_join_record(arx_handle *h) {
   ARX_CUDA(h, cudaEventRecord(h->ev_support_done, h->side_stream));
   h->support_recorded = true;
+  h->support_inflight = true;
   return ARX_OK;
 }
 // consumers of the support operands on stream st
 static int support_wait(arx_handle *h, cudaStream_t st) {
+  h->support_inflight = false;
   if (h->support_recorded) return wait_event_cap(h, st, h->ev_support_done, h->support_cid, capture_id(st));
   return ARX_OK;
 }
@@ -920,13 +924,14 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
   int32_t *chosen_ws = chosen_dev ? nullptr : reinterpret_cast<int32_t *>(static_cast<char *>(h->ws) + sz.bytes);
   h->last_path = 2;
   bool aux_pending = false;
+  const int reserve = (h->support_inflight && big_batch && (h->tc_variant & 32768) == 0) ? h->sm_reserve_n : 0;      // debug bit 32768: no reserved SMs
   ArxScoreGraph *sg = nullptr;
   bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread && graphs_enabled(h);     // the default streams cannot be captured
   if (capturable && capture_id(st) != 0) capturable = false;      // a caller that is capturing this stream itself gets plain launches
   if (capturable && disc && from_frames && !frames_stream && chunk >= n_windows && !h->prof_on && !h->trace_buf) {
     ArxScoreGraphKey key;
     key.q = query_dev; key.lo = logits_dev; key.it = is_true_dev; key.ch = chosen_dev; key.ws = h->ws; key.n = n_windows; key.way = way;
-    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0) | (h->query_f16 ? (1 << 22) : 0);
+    key.variant = h->tc_variant | (h->pdl ? (1 << 20) : 0) | (ep_way > 0 ? (1 << 21) : 0) | (h->query_f16 ? (1 << 22) : 0) | (reserve ? (1 << 23) : 0);
     key.poly = h->attn_poly; key.stagger = h->attn_stagger; key.sgen = h->support_gen; key.wgen = h->weights_gen;
     sg = score_graph_lookup(h, key);
   }
@@ -935,6 +940,10 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
   for (int64_t b0 = 0; b0 < n_windows; b0 += chunk) {
     const int64_t n = std::min(chunk, n_windows - b0), rows = n * h->T;
     if ((rc = prof_mark(h, 0, st))) return rc;
+    // A support chain still running on the side stream (set_support right before this pass) is six small dependent kernels;
+    // the persistent front-end kernels own every SM with their shared memory, so the chain only advanced in the gaps between
+    // them and the join below waited ~25 us for it.  Leave it a few SMs of its own for the length of the front end.
+    h->sm_reserve = reserve;
     rc = score_segment(h, sg, 0, st, [&]() -> int {
       int rc = ARX_OK;
       const float alpha = ARX_SOFTMAX_LOG2E / sqrtf((float)h->D);
@@ -990,6 +999,7 @@ static int score_gen3(arx_handle *h, int ti, const float *query_dev, const float
       }
       return ARX_OK;
     });
+    h->sm_reserve = 0;
     if (rc) return rc;
     if ((rc = support_wait(h, st))) return rc;                   // join the support chain (side stream) before its operands are read
     if ((rc = prof_mark(h, 3, st))) return rc;

@@ -317,7 +317,7 @@ template <int BN, int OUT, int NSTG> int launch_p(arx_handle *h, GemmPParams &p,
   const uint32_t smem = fixed + nsta * A_SUB;
   auto kern = k_gemm_p<BN, OUT, NSTG>;
   { const int rc_ = arx_func_smem(h, kern, (int)smem); if (rc_) return rc_; }
-  int grid = (h->sm_count / p.n_tiles) * p.n_tiles;
+  int grid = ((h->sm_count - h->sm_reserve) / p.n_tiles) * p.n_tiles;
   if (grid > p.m_tiles * p.n_tiles) grid = p.m_tiles * p.n_tiles;
   kern<<<grid, P_THREADS, smem, st>>>(p);
   ARX_LAUNCH_CHECK(h);
@@ -359,7 +359,7 @@ int arx_tuple_img(arx_handle *h, const ArxTransformer &tr, const float *gc, int 
   }
   const uint32_t smem = 65536 + 16 * TI_STRIDE * 4 + 1024 + 128;
   { const int rc_ = arx_func_smem(h, k_tuple_img, (int)smem); if (rc_) return rc_; }
-  const int64_t grid = n_win < 2 * h->sm_count ? n_win : 2 * h->sm_count;
+  const int64_t grid = n_win < 2 * (h->sm_count - h->sm_reserve) ? n_win : 2 * (h->sm_count - h->sm_reserve);
   TupleParams p{};
   for (int d = 0; d < 128; ++d) { p.gs[d] = tr.ln_host[d] * alpha; p.gs[128 + d] = tr.ln_host[128 + d] * alpha; }
   p.gc = gc; p.kq_img = kq_img; p.n_chunks = n_chunks; p.n_win = (int)n_win;

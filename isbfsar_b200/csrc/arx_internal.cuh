@@ -166,6 +166,9 @@ struct arx_handle {
   uint64_t tiles_gen[ARX_MAX_TRANSFORMERS] = {0, 0, 0, 0};   // support generation the tiled operands were built for (+1)
   float mlp_bias_host[192 + 256] = {};   // host copies of the (zero padded) fc1 / fc2 biases: kernel-parameter operands of k_mlp_p
   bool mlp_bias_host_ok = false;
+  bool support_inflight = false;    // a support chain was forked onto the side stream and no scoring pass has joined it yet
+  int sm_reserve_n = 4;             // how many (environment variable ARX_SM_RESERVE overrides)
+  int sm_reserve = 0;               // SMs the persistent front-end kernels leave free (for that chain) during the current pass
   int tcn_free_a = 1;               // tiled attention, pass A: softmax groups free-running (debug key 7)
   int tcn_poly = 1;                 // tiled attention, pass A: half of the exponentials on the FMA pipe (debug key 6)
   int *tcn_diag = nullptr;          // watchdog record of the tiled attention kernel

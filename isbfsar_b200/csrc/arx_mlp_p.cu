@@ -285,7 +285,7 @@ int arx_mlp_fused(arx_handle *h, const void *x, bool f16, int64_t rows, __half *
   p.m_tiles = (int)((rows + 127) / 128); p.c_nk = c_nk; p.onehot_sub = onehot_sub; p.k16_1 = (h->J3 + 15) / 16;
   memcpy(p.b1, h->mlp_bias_host, sizeof(p.b1));
   memcpy(p.b2, h->mlp_bias_host + BN1, sizeof(p.b2));
-  const int grid = p.m_tiles < h->sm_count ? p.m_tiles : h->sm_count;
+  const int grid = p.m_tiles < h->sm_count - h->sm_reserve ? p.m_tiles : h->sm_count - h->sm_reserve;
   if (f16) {
     auto kern = k_mlp_p<__half, 45>;
     { const int rc_ = arx_func_smem(h, kern, (int)SMEM_BYTES); if (rc_) return rc_; }
