@@ -721,22 +721,33 @@ __global__ void __launch_bounds__(256) k_prep_sel_tiles(const uint32_t *__restri
 }
 
 // Head table: UAB[row][p*32 + l] = sum_d Wdr[l][d] . Gv_p[row][d] (+ bdr[l] for p == 0); rows = n_win*T, pair tuples
-__global__ void __launch_bounds__(128) k_head_uab(const float *__restrict__ G, int ldg, int voff, const float *__restrict__ dr_w,
+// Persistent over groups of four rows; Wdr is staged TRANSPOSED in shared memory once per CTA (the first version ran one CTA per row
+// with every thread walking its own weight row in global memory: 32 sectors per load, 1.9 ms for 65 536 rows -- 15 % of a T=32 score).
+// Same summation order as before (bias first, d ascending): bit-identical.
+__global__ void __launch_bounds__(256) k_head_uab(const float *__restrict__ G, int ldg, int voff, const float *__restrict__ dr_w,
                                                   const float *__restrict__ dr_b, float *__restrict__ uab, int64_t rows, int L) {
-  __shared__ float g_s[2 * DD];
-  const int64_t row = blockIdx.x;
-  if (row >= rows) return;
-  for (int e = threadIdx.x; e < 2 * DD; e += 128) g_s[e] = G[row * ldg + voff + e];
-  __syncthreads();
-  const int pp = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (pp < 2) {
-    float a = 0.f;
-    if (l < L) {
-      a = pp == 0 ? dr_b[l] : 0.f;
-      const float *w = dr_w + (size_t)l * DD;
-      for (int dd = 0; dd < DD; ++dd) a = fmaf(w[dd], g_s[pp * DD + dd], a);
+  __shared__ float wT[DD][33];                      // wT[d][l], padded: the transposing store is conflict-free too
+  __shared__ __align__(16) float g_s[4][2 * DD];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 32 * DD; e += 256) {
+    const int l = e / DD, dd = e - l * DD;
+    wT[dd][l] = l < L ? dr_w[(size_t)l * DD + dd] : 0.f;
+  }
+  const int slot = tid >> 6, pp = (tid >> 5) & 1, l = tid & 31;
+  const float bias = (pp == 0 && l < L) ? dr_b[l] : 0.f;
+  for (int64_t r0 = (int64_t)blockIdx.x * 4; r0 < rows; r0 += (int64_t)gridDim.x * 4) {
+    __syncthreads();                                // the previous group's rows have been consumed (first pass: wT is complete)
+    if (r0 + slot < rows)                           // 4 rows x 256 floats: one float4 per thread, coalesced
+      *reinterpret_cast<float4 *>(&g_s[slot][(tid & 63) * 4]) = *reinterpret_cast<const float4 *>(G + (r0 + slot) * ldg + voff + (tid & 63) * 4);
+    __syncthreads();
+    if (r0 + slot < rows) {
+      float a = bias;
+      if (l < L) {
+#pragma unroll 8
+        for (int dd = 0; dd < DD; ++dd) a = fmaf(wT[dd][l], g_s[slot][pp * DD + dd], a);
+      }
+      uab[(r0 + slot) * 64 + pp * 32 + l] = a;
     }
-    uab[row * 64 + pp * 32 + l] = a;
   }
 }
 
@@ -895,7 +906,7 @@ int arx_tcn_attention(arx_handle *h, const ArxTransformer &tr, const __half *kq_
 int arx_tcn_head_all(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int way, const int32_t *iota,
                      float *uab, float *y_all, __half *vq_ws, cudaStream_t st) {
   if (tr.c != 2 || h->T > 32 || !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "tcn_head: pair tuples with T <= 32 only");
-  k_head_uab<<<(unsigned)h->T, 128, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, h->T, h->T);
+  k_head_uab<<<(unsigned)((h->T + 3) / 4), 256, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, h->T, h->T);
   ARX_LAUNCH_CHECK(h);
   int rc = tcn_prep_vq(h, tr, uab, 64, 0, 32, h->T, 1, vq_ws, st);
   if (rc) return rc;
@@ -912,7 +923,8 @@ int arx_tcn_head_all(arx_handle *h, const ArxTransformer &tr, const __half *kq_t
 int arx_tcn_head(arx_handle *h, const ArxTransformer &tr, const __half *kq_tiles, const float *G, int ldg, int64_t n_win, const int32_t *chosen,
                  float *uab, float *y, __half *y_img, int y_nk, __half *vq_ws, cudaStream_t st) {
   if (tr.c != 2 || h->T > 32 || !tr.uc_tiles) return arx_fail(h, ARX_ERR_INVALID, "tcn_head: pair tuples with T <= 32 only");
-  k_head_uab<<<(unsigned)(n_win * h->T), 128, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, n_win * h->T, h->T);
+  k_head_uab<<<(unsigned)std::min<int64_t>((n_win * h->T + 3) / 4, 4 * h->sm_count), 256, 0, st>>>(G, ldg, tr.c * h->D, h->dr_w, h->dr_b, uab, n_win * h->T,
+                                                                                                       h->T);
   ARX_LAUNCH_CHECK(h);
   int rc = tcn_prep_vq(h, tr, uab, 64, 0, 32, h->T, n_win, vq_ws, st);
   if (rc) return rc;
