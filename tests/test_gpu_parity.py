@@ -456,6 +456,29 @@ def test_fused_frame_mlp_is_bit_identical():
         assert torch.equal(res[0][0][k], res[0][1][k])
 
 
+@pytest.mark.parametrize("variant", [16384, 32768, 8192 | 16384 | 32768])
+def test_big_batch_scheduling_variants_are_bit_identical(variant):
+    """Debug bits that only change SCHEDULING -- no L2 prefetch in the head kernel (16384), front-end kernels on every SM while the
+    support chain is still in flight (32768) -- must not change a single bit; the support set is re-processed right before
+    every scoring pass so that the reserved-SM path is the one exercised."""
+    cfg = Cfg()
+    m, sd = make_model(cfg, 0)
+    n = 2 * 148 * 8 + 77
+    support, labels, query, _ = make_episode(cfg, n, 97, "iid")
+    S, Q = torch.from_numpy(support[0]).cuda(), torch.from_numpy(query).cuda()
+    out = {}
+    for bits in (0, variant):
+        m.debug_set(0, bits)
+        for _ in range(2):                                         # second pass: the replayed graphs
+            m.set_support(poses=S)
+            lo, it = m.score(Q)
+        out[bits] = (lo.clone(), it.clone())
+    m.debug_set(0, 0)
+    assert torch.equal(out[0][0], out[variant][0]) and torch.equal(out[0][1], out[variant][1])
+    rlo, rit = TrxOracle(cfg, sd).score(support, labels, query[:64])
+    assert rel_err(out[0][0][:64].cpu(), rlo).max() < TOL_TC and rel_err(out[0][1][:64].cpu(), rit).max() < TOL_TC
+
+
 def test_streaming_host_api_matches_device_path():
     """arx_score_host_submit/_wait: several requests in flight, interleaved with blocking and device-side calls and a
     support-set change; every result equals the device path bit for bit."""
