@@ -7,10 +7,10 @@
 //   * one thread issues fc1 (N=192) into TMEM columns [0,192) and fc2 (N=256) into [256,512); fc2 starts on the
 //     first 64 hidden columns while the epilogue is still producing the others, and fc1 of tile t+1 runs under the
 //     second epilogue of tile t;
-//   * eight epilogue warps (thread == row == TMEM lane, two warps per lane quadrant splitting the columns): bias + ReLU + fp16 -> the hidden operand image in shared
-//     memory; then bias + ReLU + fp16 of fc2 into the SAME 48 KB (dead once fc2 has read it) as 4 KB staging blocks,
-//     written out with bulk stores -- the arithmetic (fp16 operands, fp32 accumulate, round-to-nearest) is exactly
-//     that of the three kernels it replaces, so the feature image is bit-identical.
+//   * eight epilogue warps (thread == row == TMEM lane, two warps per lane quadrant splitting the columns): bias + ReLU +
+//     fp16 -> the hidden operand image in shared memory; then bias + ReLU + fp16 of fc2 into the SAME 48 KB (dead once fc2
+//     has read it) as 4 KB staging blocks, written out with bulk stores -- the arithmetic (fp16 operands, fp32 accumulate,
+//     round-to-nearest) is exactly that of the three kernels it replaces, so the feature image is bit-identical.
 // The one-hot(frame position) sub-tile that carries the positional-encoding / bias table through the projection GEMM
 // (arx_gemm_p.cu) is written here as well.
 #include "arx_internal.cuh"
@@ -174,10 +174,11 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_mlp_p(const __grid_constant__ 
       if (t == 0) MTRACE(2, i, 3);
     }
   } else {
-    // ---------------- epilogue warps: thread == row of the tile == TMEM lane.  EIGHT warps, two per scheduler (with one, every
-    // dependent instruction paid its full latency: timeline trace, 1.5 K + 3 K clk per tile): warps q and q + 4 share TMEM lane
-    // quadrant q and split every 64-column sub-tile, `half` = which 32 columns.  The pair meets at a named barrier where one of
-    // them speaks for both (bulk-store groups belong to the thread that committed them: lane 0 of the half-0 warp).
+    // ---------------- epilogue warps: thread == row of the tile == TMEM lane.  EIGHT warps, two per scheduler: warps q and q + 4
+    // share TMEM lane quadrant q and split every 64-column sub-tile, `half` = which 32 columns.  The pair meets at a named barrier
+    // where one of them speaks for both (bulk-store groups belong to the thread that committed them: lane 0 of the half-0 warp).
+    // (Measured against four warps doing whole sub-tiles: the same ~1.5 K + 3 K clk per tile -- the chain is TMEM-load, fence,
+    // barrier and bulk-store latencies, not instruction issue; kept because it halves the registers live per thread.)
     const int quad = warp & 3, half = warp >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
